@@ -1,0 +1,144 @@
+/*
+ * lens_b200.h -- C ABI of liblens_b200.so, the B200 (sm_100a) implementation of
+ * the LENS inference hot path (event binning -> IAF spiking network ->
+ * similarity matrix -> sequence matching -> top-N / Recall@N).
+ *
+ * Conventions
+ *   - every function returns int: 0 = ok, <0 = bad argument (see lens_last_error()),
+ *     >0 = the cudaError_t that was raised;
+ *   - every pointer is a DEVICE pointer unless it says "host"; the caller owns
+ *     all buffers, the library owns only what lives inside an opaque handle;
+ *   - every function is asynchronous and ordered on the cudaStream_t it is given
+ *     (pass as void*: 0 = legacy default stream); none synchronises the device;
+ *   - handles are not thread-safe (one per stream / rank);
+ *   - no C++ types, no torch types, no exceptions cross this boundary;
+ *   - there is no CPU fallback: without a CUDA device every compute call fails.
+ *
+ * Reference sites (relative to the reference repo root) each entry replaces are
+ * cited per function.
+ */
+#ifndef LENS_B200_H
+#define LENS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LENS_B200_VERSION_MAJOR 0
+#define LENS_B200_VERSION_MINOR 1
+
+/* Largest per-step spike count a neuron may emit and stay exact (int8 operand). */
+#define LENS_MAX_SPIKE 127
+
+/* ---- diagnostics -------------------------------------------------------- */
+int lens_version(int *major, int *minor);
+/* thread-local, never NULL, valid until the next failing call on this thread */
+const char *lens_last_error(void);
+/* number of SMs of the current device (grid sizing helper for callers) */
+int lens_device_sm_count(int *n_sm);
+
+/* ---- K1: event binning + pooling ----------------------------------------
+ * Replaces lens/collect_data.py:186-202 (event_collector + create_images; same
+ * loop in lens/tools/manual_eventframe_generator.py:6-14) and the one-hot
+ * strided pooling conv of lens/run_model.py:130-137.
+ *
+ * Events are SoA, sorted by time: t_us[n], x[n], y[n] (polarity already merged,
+ * lens/run_speck.py:266).  Window w covers [t0 + w*window_us, t0 + (w+1)*window_us).
+ * An event is kept when (x - roi_x0, y - roi_y0) lies inside the roi x roi crop;
+ * it increments frame[(yr - index_shift) mod roi][(xr - index_shift) mod roi]
+ * (index_shift = 1 is the reference's `frame[y-1, x-1]`).  Counts are stored as
+ * uint8: wrap_u8 = 1 wraps modulo 256 (`astype(np.uint8)`), 0 saturates at 255.
+ * pooled[w][i*dims + j] = frame[k*i + c][k*j + c], dims = roi / k, c = (k/2) - 1
+ * (c = 0 when k == 1).
+ *   frames      [n_win][roi][roi] u8   (nullable)
+ *   pooled      [n_win][dims*dims] u8  (nullable)
+ *   win_events  [n_win] i32 in-ROI events per window (nullable; the reference
+ *               skips empty windows, collect_data.py:194,201-202)
+ *   win_offsets [n_win + 1] i64 scratch/out: first event index of every window
+ */
+int lens_bin_events(const uint32_t *t_us, const uint16_t *x, const uint16_t *y, int64_t n_events,
+                    uint32_t t0_us, uint32_t window_us, int roi_x0, int roi_y0, int roi, int k,
+                    int index_shift, int wrap_u8, uint8_t *frames, uint8_t *pooled,
+                    int32_t *win_events, int64_t *win_offsets, int64_t n_win, void *stream);
+
+/* Pooling alone (frames already exist, e.g. decoded PNGs):
+ * frames [n][roi][roi] u8 -> pooled [n][dims*dims] u8.  lens/run_model.py:130-137. */
+int lens_pool_frames(const uint8_t *frames, int64_t n, int roi, int k, uint8_t *pooled,
+                     void *stream);
+
+/* ---- K2 + K3: the spiking network --------------------------------------
+ * Stands where `self.sinabs_model` stands (lens/run_model.py:139-156,238):
+ *   IAF#0 -> Linear(I->F, no bias) -> IAF#1 -> Linear(F->P, no bias) -> IAF#2
+ * with sinabs IAFSqueeze semantics (spike_threshold = thr, MultiSpike,
+ * MembraneSubtract, min_v_mem = v_min), lens/src/blitnet.py:59-64 weights.
+ * The handle owns fixed-point copies of the weights and the membrane potentials
+ * v0[B][I], v1[B][F], v2[B][P], which persist across calls exactly like the
+ * reference's (it never calls reset_states()).
+ *   W_feat [F][I] f32, W_out [P][F] f32, U [T][I] f32 (the sub-sampled columns of
+ *   dataset.py:120-121's seed-50 `torch.rand(T, roi*roi)`; nullable if only
+ *   lens_snn_forward_float is used).
+ * *n_inexact (host, nullable) receives the number of weights that needed rounding
+ * to the 46-bit-per-row fixed-point grid (0 => every contraction is exact).      */
+int lens_snn_create(int I, int F, int P, int T, float thr, float v_min, const float *W_feat,
+                    const float *W_out, const float *U, int max_streams, void **handle,
+                    int64_t *n_inexact, void *stream);
+int lens_snn_destroy(void *handle);
+/* sinabs Network.reset_states(): zero all membrane potentials. */
+int lens_snn_reset(void *handle, void *stream);
+/* copy membrane potentials out (any pointer nullable): v0 [B][I], v1 [B][F], v2 [B][P] */
+int lens_snn_get_state(void *handle, float *v0, float *v1, float *v2, void *stream);
+/* overflow[0] (device, i64) counts per-step spike counts that exceeded LENS_MAX_SPIKE */
+int lens_snn_get_overflow(void *handle, int64_t *overflow, void *stream);
+
+/* mode for lens_snn_forward: which output-layer kernel runs */
+#define LENS_SNN_AUTO 0   /* pick by problem size                      */
+#define LENS_SNN_SIMT 1   /* event-driven CUDA-core kernel             */
+#define LENS_SNN_TC   2   /* tcgen05 digit-plane kernel (batched)      */
+
+/* The per-query loop of lens/run_model.py:229-246 for B independent streams of Q
+ * queries each, fed by the raster of lens/src/dataset.py:14-51,118-125:
+ *   p = pooled / 255;  input spike at step t = (U[t][i] < p[i]);  T steps per query;
+ *   counts[b][q][p] = number of output spikes of place p during query q.
+ * Continues from the handle's current state (carry-over across queries and calls).
+ *   pooled        [B][Q][I] u8
+ *   counts        [B][Q][P] f32
+ *   hidden_steps  [B][Q*T][F]  u8, nullable (debug / tests)
+ *   out_steps     [B][Q*T][P]  u8, nullable (debug / tests)                      */
+int lens_snn_forward(void *handle, const uint8_t *pooled, int B, int Q, float *counts,
+                     uint8_t *hidden_steps, uint8_t *out_steps, int mode, void *stream);
+
+/* Operator seam `sinabs_model(x)` (lens/run_model.py:238) for an arbitrary float
+ * raster: x [B][steps][I] f32 (already pooled), spikes_out [B][steps][P] f32.     */
+int lens_snn_forward_float(void *handle, const float *x, int B, int steps, float *spikes_out,
+                           void *stream);
+
+/* ---- K4: sequence matching + top-N --------------------------------------
+ * Replaces lens/run_model.py:248-254 (conv2d with eye(L), / L, transpose) and the
+ * selection half of lens/src/metrics.py:183-226 (argsort(0)[-K:]).
+ *   S [B][Q][P] f32 similarity (spike counts).  Qo = Q - L + 1, Po = P - L + 1.
+ *   D[b][r][q] = (sum_{j<L} S[b][q+j][r+j]) / L
+ *   D_out   [B][Po][Qo] f32, nullable (rows = database, as the reference returns it)
+ *   top_val [B][Qo][N] f32, top_idx [B][Qo][N] i32: the N largest D[b][.][q],
+ *           ordered by (value desc, index desc) == np.argsort(kind='stable')[-N:][::-1];
+ *           missing entries (N > Po) are -inf / -1.
+ * L >= 1 (the reference's L == 0 branch returns S itself and is handled by the caller). */
+int lens_seqmatch_topk(const float *S, int B, int Q, int P, int L, int N, float *D_out,
+                       float *top_val, int32_t *top_idx, void *stream);
+
+/* Recall@N counters (lens/src/metrics.py:213-224 + lens/run_model.py:301-302).
+ * Ground truth is either dense, gt_dense [B or 1][Po][Qo] u8 (gt_stream_stride = Po*Qo
+ * or 0 to share one matrix), or a band: gt_center [B][Qo] i32 (-1 = query has no
+ * match) with |idx - center| <= gt_tol counting as a hit.  Exactly one is non-NULL.
+ *   ns      [n_ns] host ints, ascending, each <= N (e.g. 1,5,10,15,20,25)
+ *   hits    [n_ns] i64 device, ACCUMULATED (zero it first): queries with a hit in top-n
+ *   n_valid [1]    i64 device, ACCUMULATED: queries that have at least one positive  */
+int lens_recall(const int32_t *top_idx, int B, int Qo, int Po, int N, const uint8_t *gt_dense,
+                int64_t gt_stream_stride, const int32_t *gt_center, int gt_tol, const int *ns,
+                int n_ns, int64_t *hits, int64_t *n_valid, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LENS_B200_H */

@@ -1,0 +1,211 @@
+// K4: diagonal sequence matching + top-N selection + Recall@N counters.
+//
+// Replaces lens/run_model.py:248-254 (conv2d(S, eye(L)) / L, transposed) and
+// lens/src/metrics.py:213-224 (argsort(0)[-K:] + hit test), called from
+// lens/run_model.py:301-302 for N in {1,5,10,15,20,25}.  HBM-bound: every entry of
+// the similarity matrix S[B][Q][P] is needed L times, the L reads of a row hit L2
+// (one stream's S is Q*P*4 bytes), DRAM sees it once.
+//
+// D[b][r][q] = (sum_{j<L} S[b][q+j][r+j]) / L : the partial sums are small integers
+// (spike counts), exact in fp32 in any order; the one division is IEEE (__fdiv_rn),
+// like numpy's float32 / int.  Selection order is (value desc, index desc) -- the
+// order np.argsort(kind='stable')[-N:][::-1] produces -- implemented as a 64-bit max
+// over keys (orderable(value) << 32 | index).
+#include "common.cuh"
+
+#include <climits>
+
+namespace lens {
+
+constexpr int kMatchThreads = 256;
+constexpr int kCandChunk = 2048;
+constexpr int kMaxTopN = 64;
+
+__device__ __forceinline__ uint32_t f32_orderable(float v)
+{
+    uint32_t u = __float_as_uint(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float f32_from_orderable(uint32_t u)
+{
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+// grid = B * Qo.  One CTA scores every database place for one (stream, query).
+__global__ void __launch_bounds__(kMatchThreads)
+seqmatch_topk_kernel(const float *__restrict__ S, int Q, int P, int L, int N,
+                     float *__restrict__ D_out, float *__restrict__ top_val,
+                     int32_t *__restrict__ top_idx)
+{
+    __shared__ unsigned long long cand[kCandChunk];      // keys of the current chunk of places
+    __shared__ unsigned long long best[kMaxTopN];        // running top-N (descending)
+    __shared__ unsigned long long next_best[kMaxTopN];
+    __shared__ unsigned long long warp_best[kMatchThreads / 32];
+    __shared__ unsigned long long s_winner;
+    const int Qo = Q - L + 1, Po = P - L + 1;
+    const int b = blockIdx.x / Qo, q = blockIdx.x - b * Qo;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *Sb = S + (size_t)b * Q * P;
+    const float fl = (float)L;
+    for (int i = tid; i < kMaxTopN; i += kMatchThreads) best[i] = 0ull;   // 0 = empty slot
+
+    for (int r0 = 0; r0 < Po; r0 += kCandChunk) {
+        const int nr = min(kCandChunk, Po - r0);
+        for (int i = tid; i < nr; i += kMatchThreads) {
+            const int r = r0 + i;
+            float acc = 0.0f;
+            for (int j = 0; j < L; ++j) acc += __ldg(Sb + (size_t)(q + j) * P + (r + j));
+            const float d = __fdiv_rn(acc, fl);
+            if (D_out) D_out[((size_t)b * Po + r) * Qo + q] = d;
+            cand[i] = ((unsigned long long)f32_orderable(d) << 32) | (uint32_t)r;
+        }
+        __syncthreads();
+        // N rounds of block-wide max over (running best U chunk); keys are unique
+        // (distinct place index) so exactly one slot holds the winner.
+        for (int n = 0; n < N; ++n) {
+            unsigned long long mine = 0ull;
+            int mine_pos = -1;
+            for (int i = tid; i < N + nr; i += kMatchThreads) {
+                const unsigned long long k = (i < N) ? best[i] : cand[i - N];
+                if (k > mine) { mine = k; mine_pos = i; }
+            }
+            unsigned long long wb = mine;
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long other = __shfl_xor_sync(0xffffffffu, wb, o);
+                wb = other > wb ? other : wb;
+            }
+            if (lane == 0) warp_best[warp] = wb;
+            __syncthreads();
+            if (tid == 0) {
+                unsigned long long w = 0ull;
+                for (int i = 0; i < kMatchThreads / 32; ++i) w = warp_best[i] > w ? warp_best[i] : w;
+                s_winner = w;
+                next_best[n] = w;
+            }
+            __syncthreads();
+            if (mine != 0ull && mine == s_winner) {
+                if (mine_pos < N) best[mine_pos] = 0ull;
+                else cand[mine_pos - N] = 0ull;
+            }
+            __syncthreads();
+        }
+        for (int i = tid; i < N; i += kMatchThreads) best[i] = next_best[i];
+        __syncthreads();
+    }
+    for (int n = tid; n < N; n += kMatchThreads) {
+        const unsigned long long k = best[n];
+        const size_t o = ((size_t)b * Qo + q) * N + n;
+        if (k == 0ull) {
+            top_val[o] = -INFINITY;
+            top_idx[o] = -1;
+        } else {
+            top_val[o] = f32_from_orderable((uint32_t)(k >> 32));
+            top_idx[o] = (int32_t)(uint32_t)(k & 0xffffffffull);
+        }
+    }
+}
+
+struct RecallParams {
+    const int32_t *top_idx;
+    int B, Qo, Po, N;
+    const uint8_t *gt_dense;
+    int64_t gt_stream_stride;
+    const int32_t *gt_center;
+    int gt_tol;
+    int ns[8];
+    int n_ns;
+    unsigned long long *hits, *n_valid;
+};
+
+// One thread per (stream, query).  metrics.py:214-216 drops queries without any
+// positive; :218-224 counts a query as recalled when one of its K best is positive.
+__global__ void __launch_bounds__(256) recall_kernel(RecallParams p)
+{
+    __shared__ unsigned int s_hits[8];
+    __shared__ unsigned int s_valid;
+    if (threadIdx.x < 8) s_hits[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_valid = 0;
+    __syncthreads();
+    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (g < (int64_t)p.B * p.Qo) {
+        const int b = (int)(g / p.Qo), q = (int)(g - (int64_t)b * p.Qo);
+        const int32_t *ti = p.top_idx + (size_t)g * p.N;
+        bool valid;
+        int first_hit = INT_MAX;   // rank of the best-ranked positive among the top N
+        if (p.gt_dense) {
+            const uint8_t *gt = p.gt_dense + (size_t)b * p.gt_stream_stride;
+            valid = false;
+            for (int r = 0; r < p.Po; ++r) valid |= gt[(size_t)r * p.Qo + q] != 0;
+            if (valid)
+                for (int n = 0; n < p.N; ++n) {
+                    const int r = ti[n];
+                    if (r >= 0 && gt[(size_t)r * p.Qo + q] != 0) { first_hit = n; break; }
+                }
+        } else {
+            const int c = p.gt_center[g];
+            valid = c >= 0;
+            if (valid)
+                for (int n = 0; n < p.N; ++n) {
+                    const int r = ti[n];
+                    if (r >= 0 && abs(r - c) <= p.gt_tol) { first_hit = n; break; }
+                }
+        }
+        if (valid) {
+            atomicAdd(&s_valid, 1u);
+            for (int i = 0; i < p.n_ns; ++i)
+                if (first_hit < p.ns[i]) atomicAdd(&s_hits[i], 1u);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < p.n_ns && s_hits[threadIdx.x])
+        atomicAdd(p.hits + threadIdx.x, (unsigned long long)s_hits[threadIdx.x]);
+    if (threadIdx.x == 0 && s_valid) atomicAdd(p.n_valid, (unsigned long long)s_valid);
+}
+
+}  // namespace lens
+
+using namespace lens;
+
+extern "C" int lens_seqmatch_topk(const float *S, int B, int Q, int P, int L, int N, float *D_out,
+                                  float *top_val, int32_t *top_idx, void *stream)
+{
+    LENS_CHECK_ARG(B >= 0 && Q > 0 && P > 0, "lens_seqmatch_topk: bad sizes");
+    LENS_CHECK_ARG(L >= 1 && L <= Q && L <= P, "lens_seqmatch_topk: need 1 <= L <= min(Q, P), got L=%d", L);
+    LENS_CHECK_ARG(N >= 1 && N <= kMaxTopN, "lens_seqmatch_topk: N=%d outside [1, %d]", N, kMaxTopN);
+    LENS_CHECK_ARG(B == 0 || (S && top_val && top_idx), "lens_seqmatch_topk: NULL buffer");
+    LENS_CHECK_ARG((int64_t)B * (Q - L + 1) <= 2147483647LL, "lens_seqmatch_topk: too many (stream, query) pairs");
+    if (B == 0) return 0;
+    dim3 grid((unsigned)((int64_t)B * (Q - L + 1)));
+    seqmatch_topk_kernel<<<grid, kMatchThreads, 0, as_stream(stream)>>>(S, Q, P, L, N, D_out, top_val,
+                                                                        top_idx);
+    LENS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int lens_recall(const int32_t *top_idx, int B, int Qo, int Po, int N,
+                           const uint8_t *gt_dense, int64_t gt_stream_stride,
+                           const int32_t *gt_center, int gt_tol, const int *ns, int n_ns,
+                           int64_t *hits, int64_t *n_valid, void *stream)
+{
+    LENS_CHECK_ARG(B >= 0 && Qo > 0 && Po > 0 && N >= 1, "lens_recall: bad sizes");
+    LENS_CHECK_ARG((gt_dense != nullptr) != (gt_center != nullptr),
+                   "lens_recall: exactly one of gt_dense / gt_center must be given");
+    LENS_CHECK_ARG(ns && n_ns >= 1 && n_ns <= 8, "lens_recall: n_ns must be in [1, 8]");
+    LENS_CHECK_ARG(top_idx && hits && n_valid, "lens_recall: NULL buffer");
+    RecallParams p;
+    p.top_idx = top_idx; p.B = B; p.Qo = Qo; p.Po = Po; p.N = N;
+    p.gt_dense = gt_dense; p.gt_stream_stride = gt_stream_stride;
+    p.gt_center = gt_center; p.gt_tol = gt_tol; p.n_ns = n_ns;
+    for (int i = 0; i < 8; ++i) p.ns[i] = 0;
+    for (int i = 0; i < n_ns; ++i) {
+        LENS_CHECK_ARG(ns[i] >= 1 && ns[i] <= N, "lens_recall: ns[%d]=%d outside [1, N=%d]", i, ns[i], N);
+        p.ns[i] = ns[i];
+    }
+    p.hits = reinterpret_cast<unsigned long long *>(hits);
+    p.n_valid = reinterpret_cast<unsigned long long *>(n_valid);
+    if (B == 0) return 0;
+    int64_t total = (int64_t)B * Qo;
+    recall_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, as_stream(stream)>>>(p);
+    LENS_LAUNCH_CHECK();
+    return 0;
+}

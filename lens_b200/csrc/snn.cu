@@ -1,0 +1,497 @@
+// K2 + K3 (CUDA-core path): the converted sinabs network of lens/run_model.py:139-156
+//   IAF#0 -> Linear(I->F) -> IAF#1 -> Linear(F->P) -> IAF#2
+// and the per-query loop of lens/run_model.py:229-246, for B independent streams.
+//
+// Arithmetic contract (DESIGN.md "exact contraction"): both Linear contractions are
+// evaluated EXACTLY -- spikes are small integers, weights are converted once to a
+// per-row fixed-point grid (w = m * 2^q, |m| < 2^46, lossless for every weight whose
+// exponent lies within 22 bits of the row maximum), the products are accumulated in
+// int64 and rounded once to fp32 (round-to-nearest-even).  The result is the
+// correctly rounded value of sum_k s_k * w_k, independent of summation order, so the
+// event-driven kernel below, the tcgen05 digit-plane kernel (snn_tc.cu) and the CPU
+// oracle agree bit for bit.  The IAF update itself is elementwise IEEE fp32.
+//
+// Time is serial per (stream, neuron) because of the membrane recurrence; the
+// parallel axes are streams and neurons.  Layers are feed-forward, so the feature
+// layer of a stream runs ahead over all its steps (feature_kernel) and leaves the
+// hidden spikes as int8 rows in HBM for the output layer (output_simt_kernel here,
+// or the tensor-core kernel).  Both kernels keep their membrane potential in a
+// register for the whole launch; spikes are sparse (~3 % of inputs, ~4 % of hidden
+// units fire per step), so the CUDA-core contraction is event driven: per step the
+// active (index, count) pairs are compacted in shared memory and every thread adds
+// the matching weight column entries.
+#include "snn.cuh"
+
+#include <algorithm>
+#include <climits>
+
+namespace lens {
+
+// --------------------------------------------------------------------------------
+// weights -> fixed point
+// --------------------------------------------------------------------------------
+// One CTA per output neuron n.  W [n_out][n_in] f32  ->  fx [n_in][n_out] i64, scale [n_out].
+__global__ void __launch_bounds__(256) weights_to_fixed_kernel(const float *__restrict__ W,
+                                                               int n_out, int n_in,
+                                                               int64_t *__restrict__ fx,
+                                                               float *__restrict__ scale,
+                                                               int64_t *__restrict__ n_inexact)
+{
+    __shared__ int s_emax;
+    const int n = blockIdx.x;
+    if (threadIdx.x == 0) s_emax = INT_MIN;
+    __syncthreads();
+    int emax = INT_MIN;
+    for (int k = threadIdx.x; k < n_in; k += blockDim.x) {
+        uint32_t u = __float_as_uint(W[(size_t)n * n_in + k]);
+        int ef = (u >> 23) & 255;
+        uint32_t frac = u & 0x7fffffu;
+        if (ef == 255 || (ef == 0 && frac == 0)) continue;          // inf/nan/zero
+        int e = (ef == 0 ? -149 : ef - 150) + 24;                   // |w| < 2^e
+        emax = max(emax, e);
+    }
+    for (int o = 16; o > 0; o >>= 1) emax = max(emax, __shfl_xor_sync(0xffffffffu, emax, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(&s_emax, emax);
+    __syncthreads();
+    emax = s_emax;
+    int q = (emax == INT_MIN) ? 0 : emax - kFxBits;
+    if (q < -126) q = -126;                                          // keep 2^q a normal float
+    if (threadIdx.x == 0) scale[n] = __uint_as_float((uint32_t)(q + 127) << 23);
+    int64_t bad = 0;
+    for (int k = threadIdx.x; k < n_in; k += blockDim.x) {
+        uint32_t u = __float_as_uint(W[(size_t)n * n_in + k]);
+        int ef = (u >> 23) & 255;
+        uint32_t frac = u & 0x7fffffu;
+        int64_t m = 0;
+        if (ef == 255) {
+            ++bad;                                                   // inf / nan -> 0, flagged
+        } else if (!(ef == 0 && frac == 0)) {
+            int64_t mant = (ef == 0) ? (int64_t)frac : (int64_t)(frac | 0x800000u);
+            int e_ulp = (ef == 0) ? -149 : ef - 150;                 // w = mant * 2^e_ulp
+            int sh = e_ulp - q;
+            if (sh >= 0) {
+                m = mant << sh;                                      // sh <= 22 by construction
+            } else {
+                int r = -sh;
+                if (r > 26) { m = 0; ++bad; }
+                else {
+                    int64_t keep = mant >> r, rem = mant & ((1ll << r) - 1), half = 1ll << (r - 1);
+                    if (rem > half || (rem == half && (keep & 1))) ++keep;   // RNE
+                    if (rem) ++bad;
+                    m = keep;
+                }
+            }
+            if (u >> 31) m = -m;
+        }
+        fx[(size_t)k * n_out + n] = m;
+    }
+    for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd((unsigned long long *)n_inexact, (unsigned long long)bad);
+}
+
+// --------------------------------------------------------------------------------
+// event list helpers
+// --------------------------------------------------------------------------------
+// Compact the non-zero entries of `row[0..n)` (one byte per neuron) into (idx, cnt)
+// lists; executed by one full warp.  Returns the number of active entries.
+__device__ __forceinline__ int warp_compact(const uint8_t *row, int n, uint16_t *idx, uint8_t *cnt)
+{
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+        int i = i0 + lane;
+        uint8_t v = (i < n) ? row[i] : (uint8_t)0;
+        unsigned m = __ballot_sync(0xffffffffu, v != 0);
+        if (v) {
+            int pos = base + __popc(m & ((1u << lane) - 1));
+            idx[pos] = (uint16_t)i;
+            cnt[pos] = v;
+        }
+        base += __popc(m);
+    }
+    return base;
+}
+
+constexpr int kChunk = 16;   // timesteps processed between block-wide synchronisations
+
+struct FeatureParams {
+    int I, F, Fp, T;
+    float thr, vmin;
+    const int64_t *Wf_fx;     // [I][F]
+    const float *Wf_scale;    // [F]
+    const float *U;           // [T][I]
+    const uint8_t *pooled;    // [B][Q][I]           (raster mode)
+    const float *xin;         // [B][steps][I]       (float mode), exactly one of the two
+    int steps;                // per stream (= Q*T in raster mode)
+    float *v0, *v1;           // state, already offset to the first stream of this launch
+    int8_t *S1;               // [nb][steps][Fp]
+    uint8_t *hidden_steps;    // nullable [nb][steps][F]
+    int64_t *overflow;
+};
+
+// grid = streams, block = round_up(max(I, F), 32) threads.  Thread i < I owns input
+// neuron i (IAF#0), thread f < F owns feature neuron f (IAF#1).
+__global__ void __launch_bounds__(1024) feature_kernel(FeatureParams p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const int I = p.I, F = p.F;
+    const int Ipad = (I + 31) & ~31;
+    uint8_t *s0 = smem_raw;                                    // [kChunk][Ipad] input spikes
+    uint16_t *l_idx = reinterpret_cast<uint16_t *>(s0 + kChunk * Ipad);   // [kChunk][Ipad]
+    uint8_t *l_cnt = reinterpret_cast<uint8_t *>(l_idx + kChunk * Ipad);  // [kChunk][Ipad]
+    int *n_act = reinterpret_cast<int *>(l_cnt + kChunk * Ipad);          // [kChunk]
+
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const float thr = p.thr, vmin = p.vmin;
+    float v0 = (tid < I) ? p.v0[(size_t)b * I + tid] : 0.0f;
+    float v1 = (tid < F) ? p.v1[(size_t)b * F + tid] : 0.0f;
+    const float scale = (tid < F) ? p.Wf_scale[tid] : 0.0f;
+    int64_t n_over = 0;
+    float prob = 0.0f;
+
+    for (int t0 = 0; t0 < p.steps; t0 += kChunk) {
+        const int nc = min(kChunk, p.steps - t0);
+        // ---- phase A: IAF#0 over the chunk (elementwise, no cross-thread dependency)
+        if (tid < I) {
+            for (int c = 0; c < nc; ++c) {
+                const int step = t0 + c;
+                float xin;
+                if (p.pooled) {
+                    const int q = step / p.T, t = step - q * p.T;
+                    if (t == 0 || c == 0)   // lens/src/dataset.py:23  p = u8 / 255 (fp32 division)
+                        prob = __fdiv_rn((float)p.pooled[((size_t)b * (p.steps / p.T) + q) * I + tid], 255.0f);
+                    xin = (__ldg(p.U + (size_t)t * I + tid) < prob) ? 1.0f : 0.0f;  // dataset.py:121
+                } else {
+                    xin = p.xin[((size_t)b * p.steps + step) * I + tid];
+                }
+                float s = iaf_step(v0, xin, thr, vmin);
+                if (s > (float)LENS_MAX_SPIKE) { s = (float)LENS_MAX_SPIKE; ++n_over; }
+                s0[c * Ipad + tid] = (uint8_t)s;
+            }
+        }
+        __syncthreads();
+        // ---- phase B: per-step active lists
+        for (int c = warp; c < nc; c += nwarps) {
+            int n = warp_compact(s0 + c * Ipad, I, l_idx + c * Ipad, l_cnt + c * Ipad);
+            if ((tid & 31) == 0) n_act[c] = n;
+        }
+        __syncthreads();
+        // ---- phase C: exact contraction + IAF#1
+        if (tid < F) {
+            for (int c = 0; c < nc; ++c) {
+                const int n = n_act[c];
+                int64_t acc = 0;
+                for (int a = 0; a < n; ++a) {
+                    const int i = l_idx[c * Ipad + a];
+                    const int64_t s = l_cnt[c * Ipad + a];
+                    acc += s * __ldg(p.Wf_fx + (size_t)i * F + tid);
+                }
+                const float x = __fmul_rn(__ll2float_rn(acc), scale);
+                float s = iaf_step(v1, x, thr, vmin);
+                if (s > (float)LENS_MAX_SPIKE) { s = (float)LENS_MAX_SPIKE; ++n_over; }
+                const size_t row = (size_t)b * p.steps + t0 + c;
+                p.S1[row * p.Fp + tid] = (int8_t)s;
+                if (p.hidden_steps) p.hidden_steps[row * F + tid] = (uint8_t)s;
+            }
+        } else if (tid < p.Fp) {   // zero the K padding once per row
+            for (int c = 0; c < nc; ++c)
+                p.S1[((size_t)b * p.steps + t0 + c) * p.Fp + tid] = 0;
+        }
+        __syncthreads();
+    }
+    if (tid < I) p.v0[(size_t)b * I + tid] = v0;
+    if (tid < F) p.v1[(size_t)b * F + tid] = v1;
+    if (n_over) atomicAdd((unsigned long long *)p.overflow, (unsigned long long)n_over);
+}
+
+struct OutputParams {
+    int F, Fp, P, T;
+    float thr, vmin;
+    const int64_t *Wo_fx;    // [F][P]
+    const float *Wo_scale;   // [P]
+    const int8_t *S1;        // [nb][steps][Fp]
+    int steps;
+    float *v2;               // state, offset to first stream of the launch
+    float *counts;           // [nb][steps/T][P], nullable
+    float *spikes_out;       // [nb][steps][P] f32, nullable (operator seam)
+    uint8_t *out_steps;      // [nb][steps][P] u8, nullable (debug)
+};
+
+constexpr int kOutThreads = 128;
+
+// grid = (streams, place tiles); block = 128 threads, thread owns one place.
+__global__ void __launch_bounds__(kOutThreads) output_simt_kernel(OutputParams p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const int Fp = p.Fp, F = p.F, P = p.P;
+    uint8_t *s1 = smem_raw;                                               // [kChunk][Fp]
+    uint16_t *l_idx = reinterpret_cast<uint16_t *>(s1 + kChunk * Fp);     // [kChunk][Fp]
+    uint8_t *l_cnt = reinterpret_cast<uint8_t *>(l_idx + kChunk * Fp);    // [kChunk][Fp]
+    int *n_act = reinterpret_cast<int *>(l_cnt + kChunk * Fp);            // [kChunk]
+
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int place = blockIdx.y * kOutThreads + tid;
+    const bool live = place < P;
+    const float thr = p.thr, vmin = p.vmin;
+    float v2 = live ? p.v2[(size_t)b * P + place] : 0.0f;
+    const float scale = live ? p.Wo_scale[place] : 0.0f;
+    const int64_t *wcol = p.Wo_fx + (live ? place : 0);
+    float count = 0.0f;
+    const int Q = p.steps / p.T;
+
+    for (int t0 = 0; t0 < p.steps; t0 += kChunk) {
+        const int nc = min(kChunk, p.steps - t0);
+        // stage the chunk's hidden-spike rows (contiguous nc*Fp bytes) with 16-byte loads
+        {
+            const uint4 *src = reinterpret_cast<const uint4 *>(p.S1 + ((size_t)b * p.steps + t0) * Fp);
+            uint4 *dst = reinterpret_cast<uint4 *>(s1);
+            const int n16 = nc * Fp / 16;
+            for (int i = tid; i < n16; i += kOutThreads) dst[i] = __ldg(src + i);
+        }
+        __syncthreads();
+        for (int c = warp; c < nc; c += kOutThreads / 32) {
+            int n = warp_compact(s1 + c * Fp, F, l_idx + c * Fp, l_cnt + c * Fp);
+            if ((tid & 31) == 0) n_act[c] = n;
+        }
+        __syncthreads();
+        if (live) {
+            for (int c = 0; c < nc; ++c) {
+                const int n = n_act[c];
+                int64_t acc = 0;
+                for (int a = 0; a < n; ++a) {
+                    const int k = l_idx[c * Fp + a];
+                    const int64_t s = l_cnt[c * Fp + a];
+                    acc += s * __ldg(wcol + (size_t)k * P);
+                }
+                const float x = __fmul_rn(__ll2float_rn(acc), scale);
+                const float s = iaf_step(v2, x, thr, vmin);
+                const int step = t0 + c;
+                const size_t row = (size_t)b * p.steps + step;
+                if (p.spikes_out) p.spikes_out[row * P + place] = s;
+                if (p.out_steps) p.out_steps[row * P + place] = (uint8_t)fminf(s, 255.0f);
+                if (p.counts) {
+                    count += s;                                   // run_model.py:239 sum over T
+                    const int q = step / p.T;
+                    if (step - q * p.T == p.T - 1) {
+                        p.counts[((size_t)b * Q + q) * P + place] = count;
+                        count = 0.0f;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (live) p.v2[(size_t)b * P + place] = v2;
+}
+
+static int launch_feature(SnnHandle *h, const uint8_t *pooled, const float *xin, int b0, int nb,
+                          int steps, uint8_t *hidden_steps, cudaStream_t st)
+{
+    FeatureParams p;
+    p.I = h->I; p.F = h->F; p.Fp = h->Fp; p.T = h->T; p.thr = h->thr; p.vmin = h->vmin;
+    p.Wf_fx = h->Wf_fx; p.Wf_scale = h->Wf_scale; p.U = h->U;
+    p.pooled = pooled; p.xin = xin; p.steps = steps;
+    p.v0 = h->v0 + (size_t)b0 * h->I; p.v1 = h->v1 + (size_t)b0 * h->F;
+    p.S1 = h->S1; p.hidden_steps = hidden_steps; p.overflow = h->counters;
+    int threads = (std::max(std::max(h->I, h->Fp), 32) + 31) & ~31;
+    int Ipad = (h->I + 31) & ~31;
+    size_t smem = (size_t)kChunk * Ipad * 4 + kChunk * sizeof(int);
+    feature_kernel<<<nb, threads, smem, st>>>(p);
+    LENS_LAUNCH_CHECK();
+    return 0;
+}
+
+static int launch_output_simt(SnnHandle *h, int b0, int nb, int steps, float *counts,
+                              float *spikes_out, uint8_t *out_steps, cudaStream_t st)
+{
+    OutputParams p;
+    p.F = h->F; p.Fp = h->Fp; p.P = h->P; p.T = h->T; p.thr = h->thr; p.vmin = h->vmin;
+    p.Wo_fx = h->Wo_fx; p.Wo_scale = h->Wo_scale; p.S1 = h->S1; p.steps = steps;
+    p.v2 = h->v2 + (size_t)b0 * h->P;
+    p.counts = counts; p.spikes_out = spikes_out; p.out_steps = out_steps;
+    size_t smem = (size_t)kChunk * h->Fp * 4 + kChunk * sizeof(int);
+    dim3 grid(nb, ceil_div(h->P, kOutThreads));
+    output_simt_kernel<<<grid, kOutThreads, smem, st>>>(p);
+    LENS_LAUNCH_CHECK();
+    return 0;
+}
+
+static int ensure_scratch(SnnHandle *h, size_t bytes)
+{
+    if (bytes <= h->S1_cap) return 0;
+    if (h->S1) LENS_CUDA(cudaFree(h->S1));
+    h->S1 = nullptr; h->S1_cap = 0;
+    LENS_CUDA(cudaMalloc(&h->S1, bytes));
+    h->S1_cap = bytes;
+    return 0;
+}
+
+// Streams are processed in groups so the hidden-spike scratch stays bounded.
+static size_t scratch_budget() { return (size_t)6 << 30; }
+
+static int forward_common(SnnHandle *h, const uint8_t *pooled, const float *xin, int B, int steps,
+                          float *counts, float *spikes_out, uint8_t *hidden_steps,
+                          uint8_t *out_steps, int mode, cudaStream_t st)
+{
+    const size_t per_stream = (size_t)steps * h->Fp;
+    int group = (int)std::min<size_t>((size_t)B, std::max<size_t>((size_t)1, scratch_budget() / std::max<size_t>(per_stream, 1)));
+    int rc = ensure_scratch(h, per_stream * group);
+    if (rc) return rc;
+    const int Q = steps / h->T;
+    bool use_tc = false;
+    if (mode == LENS_SNN_TC) use_tc = true;
+    else if (mode == LENS_SNN_AUTO) use_tc = snn_tc_supported(h) && !spikes_out && (size_t)B * h->P >= (size_t)64 * 1024;
+    if (use_tc) {
+        LENS_CHECK_ARG(snn_tc_supported(h) && !spikes_out,
+                       "lens_snn_forward: tensor-core mode unavailable for this shape");
+        rc = snn_tc_prepare(h, st);
+        if (rc) return rc;
+    }
+    for (int b0 = 0; b0 < B; b0 += group) {
+        const int nb = std::min(group, B - b0);
+        rc = launch_feature(h, pooled ? pooled + (size_t)b0 * Q * h->I : nullptr,
+                            xin ? xin + (size_t)b0 * steps * h->I : nullptr, b0, nb, steps,
+                            hidden_steps ? hidden_steps + (size_t)b0 * steps * h->F : nullptr, st);
+        if (rc) return rc;
+        float *c = counts ? counts + (size_t)b0 * Q * h->P : nullptr;
+        uint8_t *os = out_steps ? out_steps + (size_t)b0 * steps * h->P : nullptr;
+        if (use_tc)
+            rc = snn_tc_output(h, h->S1, nb, b0, steps, c, os, st);
+        else
+            rc = launch_output_simt(h, b0, nb, steps, c,
+                                    spikes_out ? spikes_out + (size_t)b0 * steps * h->P : nullptr, os, st);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+}  // namespace lens
+
+using namespace lens;
+
+extern "C" int lens_snn_create(int I, int F, int P, int T, float thr, float v_min,
+                               const float *W_feat, const float *W_out, const float *U,
+                               int max_streams, void **handle, int64_t *n_inexact, void *stream)
+{
+    LENS_CHECK_ARG(handle != nullptr, "lens_snn_create: handle is NULL");
+    *handle = nullptr;
+    LENS_CHECK_ARG(I > 0 && F > 0 && P > 0 && T > 0 && max_streams > 0, "lens_snn_create: bad sizes");
+    LENS_CHECK_ARG(I <= 1024 && F <= 992, "lens_snn_create: I=%d F=%d exceed the supported 1024/992", I, F);
+    LENS_CHECK_ARG(W_feat && W_out, "lens_snn_create: NULL weights");
+    LENS_CHECK_ARG(thr > 0.0f, "lens_snn_create: threshold must be positive");
+    cudaStream_t st = as_stream(stream);
+    SnnHandle *h = new SnnHandle();
+    h->I = I; h->F = F; h->P = P; h->T = T; h->thr = thr; h->vmin = v_min; h->maxB = max_streams;
+    h->Fp = (F + kHiddenPad - 1) / kHiddenPad * kHiddenPad;
+    cudaGetDevice(&h->device);
+#define H_CUDA(call)                                                                   \
+    do {                                                                               \
+        cudaError_t e__ = (call);                                                      \
+        if (e__ != cudaSuccess) {                                                      \
+            set_err("lens_snn_create: %s -> %s", #call, cudaGetErrorString(e__));      \
+            lens_snn_destroy(h);                                                       \
+            return (int)e__;                                                           \
+        }                                                                              \
+    } while (0)
+    H_CUDA(cudaMalloc(&h->Wf_fx, (size_t)I * F * sizeof(int64_t)));
+    H_CUDA(cudaMalloc(&h->Wf_scale, (size_t)F * sizeof(float)));
+    H_CUDA(cudaMalloc(&h->Wo_fx, (size_t)F * P * sizeof(int64_t)));
+    H_CUDA(cudaMalloc(&h->Wo_scale, (size_t)P * sizeof(float)));
+    H_CUDA(cudaMalloc(&h->counters, 2 * sizeof(int64_t)));
+    H_CUDA(cudaMemsetAsync(h->counters, 0, 2 * sizeof(int64_t), st));
+    if (U) {
+        H_CUDA(cudaMalloc(&h->U, (size_t)T * I * sizeof(float)));
+        H_CUDA(cudaMemcpyAsync(h->U, U, (size_t)T * I * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    H_CUDA(cudaMalloc(&h->v0, (size_t)max_streams * I * sizeof(float)));
+    H_CUDA(cudaMalloc(&h->v1, (size_t)max_streams * F * sizeof(float)));
+    H_CUDA(cudaMalloc(&h->v2, (size_t)max_streams * P * sizeof(float)));
+    H_CUDA(cudaMemsetAsync(h->v0, 0, (size_t)max_streams * I * sizeof(float), st));
+    H_CUDA(cudaMemsetAsync(h->v1, 0, (size_t)max_streams * F * sizeof(float), st));
+    H_CUDA(cudaMemsetAsync(h->v2, 0, (size_t)max_streams * P * sizeof(float), st));
+    weights_to_fixed_kernel<<<F, 256, 0, st>>>(W_feat, F, I, h->Wf_fx, h->Wf_scale, h->counters + 1);
+    H_CUDA(cudaGetLastError());
+    weights_to_fixed_kernel<<<P, 256, 0, st>>>(W_out, P, F, h->Wo_fx, h->Wo_scale, h->counters + 1);
+    H_CUDA(cudaGetLastError());
+    if (n_inexact) {   // the one synchronising call of the API (construction time only)
+        H_CUDA(cudaMemcpyAsync(n_inexact, h->counters + 1, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        H_CUDA(cudaStreamSynchronize(st));
+    }
+#undef H_CUDA
+    *handle = h;
+    return 0;
+}
+
+extern "C" int lens_snn_destroy(void *handle)
+{
+    if (!handle) return 0;
+    SnnHandle *h = static_cast<SnnHandle *>(handle);
+    snn_tc_release(h);
+    cudaFree(h->Wf_fx); cudaFree(h->Wf_scale); cudaFree(h->Wo_fx); cudaFree(h->Wo_scale);
+    cudaFree(h->U); cudaFree(h->v0); cudaFree(h->v1); cudaFree(h->v2);
+    cudaFree(h->counters); cudaFree(h->S1);
+    delete h;
+    return 0;
+}
+
+extern "C" int lens_snn_reset(void *handle, void *stream)
+{
+    LENS_CHECK_ARG(handle, "lens_snn_reset: NULL handle");
+    SnnHandle *h = static_cast<SnnHandle *>(handle);
+    cudaStream_t st = as_stream(stream);
+    LENS_CUDA(cudaMemsetAsync(h->v0, 0, (size_t)h->maxB * h->I * sizeof(float), st));
+    LENS_CUDA(cudaMemsetAsync(h->v1, 0, (size_t)h->maxB * h->F * sizeof(float), st));
+    LENS_CUDA(cudaMemsetAsync(h->v2, 0, (size_t)h->maxB * h->P * sizeof(float), st));
+    LENS_CUDA(cudaMemsetAsync(h->counters, 0, sizeof(int64_t), st));
+    return 0;
+}
+
+extern "C" int lens_snn_get_state(void *handle, float *v0, float *v1, float *v2, void *stream)
+{
+    LENS_CHECK_ARG(handle, "lens_snn_get_state: NULL handle");
+    SnnHandle *h = static_cast<SnnHandle *>(handle);
+    cudaStream_t st = as_stream(stream);
+    if (v0) LENS_CUDA(cudaMemcpyAsync(v0, h->v0, (size_t)h->maxB * h->I * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (v1) LENS_CUDA(cudaMemcpyAsync(v1, h->v1, (size_t)h->maxB * h->F * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (v2) LENS_CUDA(cudaMemcpyAsync(v2, h->v2, (size_t)h->maxB * h->P * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+extern "C" int lens_snn_get_overflow(void *handle, int64_t *overflow, void *stream)
+{
+    LENS_CHECK_ARG(handle && overflow, "lens_snn_get_overflow: NULL argument");
+    SnnHandle *h = static_cast<SnnHandle *>(handle);
+    LENS_CUDA(cudaMemcpyAsync(overflow, h->counters, sizeof(int64_t), cudaMemcpyDeviceToDevice, as_stream(stream)));
+    return 0;
+}
+
+extern "C" int lens_snn_forward(void *handle, const uint8_t *pooled, int B, int Q, float *counts,
+                                uint8_t *hidden_steps, uint8_t *out_steps, int mode, void *stream)
+{
+    LENS_CHECK_ARG(handle, "lens_snn_forward: NULL handle");
+    SnnHandle *h = static_cast<SnnHandle *>(handle);
+    LENS_CHECK_ARG(h->U != nullptr, "lens_snn_forward: handle was created without the raster matrix U");
+    LENS_CHECK_ARG(B >= 0 && Q >= 0 && B <= h->maxB, "lens_snn_forward: B=%d exceeds max_streams=%d", B, h->maxB);
+    LENS_CHECK_ARG(mode >= LENS_SNN_AUTO && mode <= LENS_SNN_TC, "lens_snn_forward: bad mode %d", mode);
+    if (B == 0 || Q == 0) return 0;
+    LENS_CHECK_ARG(pooled && counts, "lens_snn_forward: NULL buffer");
+    LENS_CHECK_ARG((int64_t)Q * h->T <= 2147483647LL, "lens_snn_forward: too many steps");
+    return forward_common(h, pooled, nullptr, B, Q * h->T, counts, nullptr, hidden_steps, out_steps,
+                          mode, as_stream(stream));
+}
+
+extern "C" int lens_snn_forward_float(void *handle, const float *x, int B, int steps,
+                                      float *spikes_out, void *stream)
+{
+    LENS_CHECK_ARG(handle, "lens_snn_forward_float: NULL handle");
+    SnnHandle *h = static_cast<SnnHandle *>(handle);
+    LENS_CHECK_ARG(B >= 0 && steps >= 0 && B <= h->maxB, "lens_snn_forward_float: B=%d exceeds max_streams=%d", B, h->maxB);
+    if (B == 0 || steps == 0) return 0;
+    LENS_CHECK_ARG(x && spikes_out, "lens_snn_forward_float: NULL buffer");
+    return forward_common(h, nullptr, x, B, steps, nullptr, spikes_out, nullptr, nullptr,
+                          LENS_SNN_SIMT, as_stream(stream));
+}

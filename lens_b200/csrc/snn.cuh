@@ -1,0 +1,41 @@
+// Internal definitions shared by the SNN translation units (snn.cu, snn_tc.cu).
+#pragma once
+#include "common.cuh"
+
+namespace lens {
+
+// Fixed-point grid of a weight row: w = m * 2^q with |m| < 2^46 (see snn.cu).
+constexpr int kFxBits = 46;
+// Hidden-spike rows are stored as int8 padded to a multiple of 32 columns
+// (16-byte loads, and the K granularity of tcgen05 kind::i8).
+constexpr int kHiddenPad = 32;
+// Number of radix-256 balanced digits that cover the 47-bit signed fixed-point weights.
+constexpr int kPlanes = 6;
+
+struct SnnHandle {
+    int I, F, P, T, Fp, maxB;
+    float thr, vmin;
+    // CUDA-core (event-driven) operands
+    int64_t *Wf_fx = nullptr;   // [I][F]  feature weights, input-major, fixed point
+    float *Wf_scale = nullptr;  // [F]     2^q per feature neuron
+    int64_t *Wo_fx = nullptr;   // [F][P]  output weights, hidden-major, fixed point
+    float *Wo_scale = nullptr;  // [P]     2^q per place
+    float *U = nullptr;         // [T][I]  raster uniforms (nullable)
+    float *v0 = nullptr, *v1 = nullptr, *v2 = nullptr;  // membrane potentials [maxB][I|F|P]
+    int64_t *counters = nullptr;  // [0] spike overflow, [1] inexact weights
+    int8_t *S1 = nullptr;         // scratch hidden spikes [streams][steps][Fp]
+    size_t S1_cap = 0;
+    // tensor-core operands (built lazily by snn_tc.cu)
+    int8_t *Wo_planes = nullptr;  // [P_tiles][kPlanes][...] canonical UMMA layout
+    int P_tiles = 0;
+    int device = 0;
+};
+
+// snn_tc.cu
+int snn_tc_prepare(SnnHandle *h, cudaStream_t st);
+void snn_tc_release(SnnHandle *h);
+int snn_tc_output(SnnHandle *h, const int8_t *S1, int nb, int b0, int steps, float *counts,
+                  uint8_t *out_steps, cudaStream_t st);
+bool snn_tc_supported(const SnnHandle *h);
+
+}  // namespace lens

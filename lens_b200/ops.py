@@ -1,0 +1,105 @@
+"""Host-side wrappers of the C ABI (torch tensors in, torch tensors out).
+
+PyTorch is used for device memory and streams only; every computation happens in
+liblens_b200.so (hand-written sm_100a kernels).  All wrappers are asynchronous on
+torch's current CUDA stream.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr, require_cuda
+
+RECALL_NS = (1, 5, 10, 15, 20, 25)   # lens/run_model.py:266
+
+
+def pool_geometry(roi, k):
+    """dims and centre index of the one-hot strided conv (lens/run_model.py:130-137)."""
+    dims = roi // k
+    c = (k // 2) - 1
+    if c < 0:
+        c += k
+    return dims, c
+
+
+def pool_frames(frames, k):
+    """frames u8 [n, roi, roi] -> pooled u8 [n, dims*dims] (pixel pick of run_model.py:130-137)."""
+    require_cuda(frames)
+    assert frames.dtype == torch.uint8 and frames.dim() == 3 and frames.shape[1] == frames.shape[2]
+    n, roi, _ = frames.shape
+    dims, _ = pool_geometry(roi, k)
+    out = torch.empty((n, dims * dims), dtype=torch.uint8, device=frames.device)
+    check(_lib.lib().lens_pool_frames(ptr(frames), n, roi, k, ptr(out), stream_ptr()), "lens_pool_frames")
+    return out
+
+
+def bin_events(t_us, x, y, t0_us, window_us, n_win, roi, k, roi_x0=0, roi_y0=0, index_shift=1,
+               wrap_u8=True, want_frames=True, want_pooled=True):
+    """Event stream -> (frames u8 [n_win, roi, roi], pooled u8 [n_win, I], events-per-window i32).
+
+    Mirrors lens/collect_data.py:186-202 (`frame[y-1, x-1] += 1`, `.astype(np.uint8)`); the
+    caller drops windows whose count is 0 to reproduce create_images' "No events" branch.
+    """
+    require_cuda(t_us, x, y)
+    assert t_us.dtype == torch.int32 or t_us.dtype == torch.uint32
+    assert x.dtype in (torch.int16, torch.uint16) and y.dtype in (torch.int16, torch.uint16)
+    n = t_us.numel()
+    dev = t_us.device
+    dims, _ = pool_geometry(roi, k)
+    frames = torch.empty((n_win, roi, roi), dtype=torch.uint8, device=dev) if want_frames else None
+    pooled = torch.empty((n_win, dims * dims), dtype=torch.uint8, device=dev) if want_pooled else None
+    cnt = torch.empty((n_win,), dtype=torch.int32, device=dev)
+    offs = torch.empty((n_win + 1,), dtype=torch.int64, device=dev)
+    check(_lib.lib().lens_bin_events(ptr(t_us), ptr(x), ptr(y), n, t0_us, window_us, roi_x0, roi_y0,
+                                     roi, k, index_shift, int(wrap_u8), ptr(frames), ptr(pooled),
+                                     ptr(cnt), ptr(offs), n_win, stream_ptr()), "lens_bin_events")
+    return frames, pooled, cnt
+
+
+def seqmatch_topk(S, L, N=25, want_D=False):
+    """S f32 [B, Q, P] -> (top_val [B, Qo, N], top_idx [B, Qo, N], D [B, Po, Qo] or None).
+
+    lens/run_model.py:248-254 + the selection of lens/src/metrics.py:218.
+    """
+    require_cuda(S)
+    assert S.dtype == torch.float32 and S.dim() == 3
+    B, Q, P = S.shape
+    Qo, Po = Q - L + 1, P - L + 1
+    D = torch.empty((B, Po, Qo), dtype=torch.float32, device=S.device) if want_D else None
+    tv = torch.empty((B, Qo, N), dtype=torch.float32, device=S.device)
+    ti = torch.empty((B, Qo, N), dtype=torch.int32, device=S.device)
+    check(_lib.lib().lens_seqmatch_topk(ptr(S), B, Q, P, L, N, ptr(D), ptr(tv), ptr(ti), stream_ptr()),
+          "lens_seqmatch_topk")
+    return tv, ti, D
+
+
+def recall_counts(top_idx, Po, gt_dense=None, gt_center=None, gt_tol=0, ns=RECALL_NS,
+                  hits=None, n_valid=None):
+    """Accumulate Recall@N hit counters (device int64) for top_idx [B, Qo, N].
+
+    gt_dense: u8 [Po, Qo] (shared by all streams) or [B, Po, Qo]; or gt_center i32 [B, Qo].
+    Returns (hits [len(ns)] i64, n_valid [1] i64) on the device.
+    """
+    require_cuda(top_idx, gt_dense, gt_center)
+    B, Qo, N = top_idx.shape
+    dev = top_idx.device
+    if hits is None:
+        hits = torch.zeros((len(ns),), dtype=torch.int64, device=dev)
+    if n_valid is None:
+        n_valid = torch.zeros((1,), dtype=torch.int64, device=dev)
+    stride = 0
+    if gt_dense is not None:
+        assert gt_dense.dtype == torch.uint8
+        if gt_dense.dim() == 3:
+            assert gt_dense.shape == (B, Po, Qo)
+            stride = Po * Qo
+        else:
+            assert gt_dense.shape == (Po, Qo)
+    if gt_center is not None:
+        assert gt_center.dtype == torch.int32 and gt_center.shape == (B, Qo)
+    ns_arr = (C.c_int * len(ns))(*ns)
+    check(_lib.lib().lens_recall(ptr(top_idx), B, Qo, Po, N, ptr(gt_dense), stride, ptr(gt_center),
+                                 gt_tol, ns_arr, len(ns), ptr(hits), ptr(n_valid), stream_ptr()),
+          "lens_recall")
+    return hits, n_valid

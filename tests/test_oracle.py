@@ -1,0 +1,168 @@
+"""CPU tests: the oracle against the golden vectors produced by the reference's own code.
+
+Goldens: tests/golden/make_golden.py ran /root/reference's run_model.LENS.evaluate,
+dataset.CustomImageDataset and metrics.recallAtK (sinabs restated, see sinabs_stub.py).
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+
+def _setup(g):
+    roi, dims, T = int(g["roi_dim"]), int(g["dims"]), int(g["timebin"])
+    k = roi // dims
+    U = O.raster_uniforms(T, roi, k)
+    pooled = O.pool(g["frames"], k)
+    return roi, k, T, U, pooled
+
+
+def test_raster_uniforms_hash(golden):
+    import hashlib
+    import torch
+    g = golden("config1")
+    torch.manual_seed(50)
+    U = torch.rand(int(g["timebin"]), int(g["roi_dim"]) ** 2).numpy()
+    assert hashlib.sha256(U.tobytes()).hexdigest() == str(g["U_sha256"])
+    sub = O.raster_uniforms(int(g["timebin"]), int(g["roi_dim"]), 8)
+    assert np.array_equal(sub, U[:, O.pool_index(80, 8)])
+
+
+def test_pool_matches_onehot_conv():
+    import torch
+    rng = np.random.default_rng(0)
+    for roi, k in [(80, 8), (7, 1), (12, 3), (10, 2)]:
+        fr = rng.integers(0, 256, (5, roi, roi)).astype(np.uint8)
+        kern = torch.zeros(1, 1, k, k)
+        c = (k // 2) - 1
+        kern[0, 0, c, c] = 1   # lens/run_model.py:130-134 (c = -1 wraps for k = 1)
+        ref = torch.nn.functional.conv2d(torch.from_numpy(fr).float()[:, None], kern, stride=k)
+        assert np.array_equal(O.pool(fr, k), ref.reshape(5, -1).numpy().astype(np.uint8))
+
+
+def test_config1_counts_bit_exact(golden):
+    """Bundled example model + data: spike counts, hidden spikes, per-step outputs identical."""
+    g = golden("config1")
+    roi, k, T, U, pooled = _setup(g)
+    net = O.OracleSNN(g["W_feat"], g["W_out"], U, T)
+    counts, hid, out = net.run_streams(pooled[None], want_steps=True)
+    Q = pooled.shape[0]
+    assert np.array_equal(counts[0], g["S"].astype(np.float32))
+    assert np.array_equal(hid[0].reshape(Q, T, -1).sum(1), g["hidden_counts"])
+    n = g["hidden_steps"].shape[0]
+    assert np.array_equal(hid[0][:n * T].reshape(n, T, -1), g["hidden_steps"])
+    assert np.array_equal(out[0][:n * T].reshape(n, T, -1), g["out_steps"])
+    v0, v1, v2 = net.state()
+    # membrane potentials: within 1e-5 of the BLAS-ordered reference (absolute, |v| <= ~1)
+    assert np.abs(v1[0] - g["v1"]).max() < 1e-5
+    assert np.abs(v2[0] - g["v2"]).max() < 1e-5
+    assert np.array_equal(v0[0], g["v0"])
+    assert net.overflow() == 0
+
+
+def test_config1_tail_identical(golden):
+    g = golden("config1")
+    L, tol = int(g["sequence_length"]), int(g["GT_tolerance"])
+    D, GTtol, R = O.evaluate_tail(g["S"].astype(np.float64), g["GT"], L, tol)
+    assert np.array_equal(D, g["D"])
+    assert np.array_equal(GTtol, g["GTtol"])
+    assert np.allclose(R, g["R"])
+
+
+@pytest.mark.timeout(300)
+def test_brisevent_counts(golden):
+    """Second bundled model (641 places, 724 queries, k = 1).  The reference's BLAS summation
+    order moves two spikes across a query boundary (2 / 464084 entries differ by one count);
+    everything else is identical and Recall@N is the same."""
+    g = golden("brisevent")
+    roi, k, T, U, pooled = _setup(g)
+    assert k == 1
+    net = O.OracleSNN(g["W_feat"], g["W_out"], U, T)
+    counts = net.run_streams(pooled[None])[0]
+    S = g["S"].astype(np.float32)
+    diff = counts != S
+    assert diff.sum() <= 4 and np.abs(counts - S).max() <= 1
+    L, tol = int(g["sequence_length"]), int(g["GT_tolerance"])
+    D, GTtol, R = O.evaluate_tail(counts, g["GT"], L, tol)
+    assert np.array_equal(GTtol, g["GTtol"])
+    assert np.allclose(R, g["R"])
+    Dg, _, Rg = O.evaluate_tail(S, g["GT"], L, tol)
+    assert np.array_equal(Dg, g["D"]) and np.allclose(Rg, g["R"])
+
+
+def test_seqmatch_matches_conv2d():
+    import torch
+    rng = np.random.default_rng(3)
+    for Q, P, L in [(9, 11, 1), (9, 11, 2), (16, 12, 5), (10, 10, 10)]:
+        S = rng.integers(0, 40, (Q, P)).astype(np.float64)
+        t = torch.tensor(S)[None, None].to(torch.float32)
+        w = torch.eye(L)[None, None]
+        ref = torch.nn.functional.conv2d(t, w).squeeze(0).squeeze(0).numpy() / L   # run_model.py:249-252
+        ref = ref.T
+        assert np.array_equal(O.seqmatch(S, L), ref.reshape(P - L + 1, Q - L + 1))
+    assert O.seqmatch(S, 0) is not None
+
+
+def test_topk_is_stable_argsort():
+    rng = np.random.default_rng(4)
+    D = rng.integers(0, 5, (37, 9)).astype(np.float32) / 2   # many ties
+    for K in (1, 5, 25, 40):
+        idx, val = O.topk(D, K)
+        ref = np.argsort(D, axis=0, kind="stable")[-K:][::-1].T
+        kk = min(K, D.shape[0])
+        assert np.array_equal(idx[:, :kk], ref[:, :kk])
+        assert (idx[:, kk:] == -1).all()
+        assert np.array_equal(val[:, :kk], np.take_along_axis(D.T, ref[:, :kk], 1))
+
+
+def test_recall_variants(golden):
+    g = golden("config1")
+    D, GT = g["D"], g["GTtol"]
+    for K in (1, 5, 10, 25):
+        lo, hi = O.recall_bounds(D, GT, K)
+        r_def = O.recall_at_k(D, GT, K=K)
+        r_stable = O.recall_at_k(D, GT, K=K, kind="stable")
+        assert lo - 1e-12 <= r_def <= hi + 1e-12
+        assert lo - 1e-12 <= r_stable <= hi + 1e-12
+        # stable rule from the top-K lists
+        idx, _ = O.topk(D, K)
+        keep = GT.astype(bool).sum(0) > 0
+        hit = [GT[idx[q][idx[q] >= 0], q].any() for q in range(D.shape[1]) if keep[q]]
+        assert abs(np.mean(hit) - r_stable) < 1e-12
+
+
+def test_bin_events_reference_loop():
+    """Oracle binning == the literal per-event loop of collect_data.py:193-202."""
+    rng = np.random.default_rng(5)
+    roi, n = 16, 4000
+    t = np.sort(rng.integers(0, 1000, n)).astype(np.uint32)
+    x = rng.integers(0, roi, n).astype(np.uint16)
+    y = rng.integers(0, roi, n).astype(np.uint16)
+    x[:600] = 3
+    y[:600] = 0   # > 255 hits on one pixel of window 0 -> uint8 wrap; y = 0 -> row -1
+    t[:600] = 5
+    t.sort()
+    frames, pooled, cnt = O.bin_events(t, x, y, 0, 250, 4, roi, 4)
+    for w in range(4):
+        fr = np.zeros((roi, roi), dtype=np.int64)
+        sel = (t >= 250 * w) & (t < 250 * (w + 1))
+        for xe, ye in zip(x[sel].astype(int), y[sel].astype(int)):
+            fr[ye - 1, xe - 1] += 1
+        assert np.array_equal(frames[w], fr.astype(np.uint8))
+        assert cnt[w] == sel.sum()
+    assert np.array_equal(pooled, O.pool(frames, 4))
+    assert frames.astype(int).sum() != n   # the wrap really happened
+
+
+def test_forward_float_matches_raster_path(golden):
+    g = golden("config1")
+    roi, k, T, U, pooled = _setup(g)
+    Q = 3
+    a = O.OracleSNN(g["W_feat"], g["W_out"], U, T)
+    ca, _, outa = a.run_streams(pooled[None, :Q], want_steps=True)
+    b = O.OracleSNN(g["W_feat"], g["W_out"], None, T)
+    p = pooled[:Q].astype(np.float32) / np.float32(255)
+    x = (U[None] < p[:, None, :]).astype(np.float32).reshape(1, Q * T, -1)
+    sb = b.forward_float(x)
+    assert np.array_equal(sb[0], outa[0].astype(np.float32))
+    assert np.array_equal(sb[0].reshape(Q, T, -1).sum(1), ca[0])
