@@ -38,6 +38,8 @@ int lens_version(int *major, int *minor);
 const char *lens_last_error(void);
 /* number of SMs of the current device (grid sizing helper for callers) */
 int lens_device_sm_count(int *n_sm);
+/* kernels launched by this library since it was loaded (host counter; bench evidence) */
+int lens_launch_count(int64_t *n_launches);
 
 /* ---- K1: event binning + pooling ----------------------------------------
  * Replaces lens/collect_data.py:186-202 (event_collector + create_images; same
@@ -91,6 +93,13 @@ int lens_snn_reset(void *handle, void *stream);
 int lens_snn_get_state(void *handle, float *v0, float *v1, float *v2, void *stream);
 /* overflow[0] (device, i64) counts per-step spike counts that exceeded LENS_MAX_SPIKE */
 int lens_snn_get_overflow(void *handle, int64_t *overflow, void *stream);
+
+/* Optional per-kernel timing (bench.py's roofline): when enabled every feature- / output-layer
+ * launch is bracketed by cudaEvents on its own stream.  lens_snn_get_timing waits for the recorded
+ * events (host pointers), returns the accumulated milliseconds and launch counts, and clears them. */
+int lens_snn_set_timing(void *handle, int enable);
+int lens_snn_get_timing(void *handle, float *feature_ms, float *output_ms, int64_t *n_feature,
+                        int64_t *n_output);
 
 /* mode for lens_snn_forward: which output-layer kernel runs */
 #define LENS_SNN_AUTO 0   /* pick by problem size                      */

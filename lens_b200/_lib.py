@@ -22,6 +22,9 @@ def _declare(L):
         "lens_version": (i32, [pi32, pi32]),
         "lens_last_error": (C.c_char_p, []),
         "lens_device_sm_count": (i32, [pi32]),
+        "lens_launch_count": (i32, [pi64]),
+        "lens_snn_set_timing": (i32, [vp, i32]),
+        "lens_snn_get_timing": (i32, [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), pi64, pi64]),
         "lens_bin_events": (i32, [vp, vp, vp, i64, u32, u32, i32, i32, i32, i32, i32, i32,
                                   vp, vp, vp, vp, i64, vp]),
         "lens_pool_frames": (i32, [vp, i64, i32, i32, vp, vp]),
@@ -87,3 +90,10 @@ def require_cuda(*tensors):
     for t in tensors:
         if t is not None and (not t.is_cuda or not t.is_contiguous()):
             raise LensError("lens_b200 expects contiguous CUDA tensors")
+
+
+def launch_count():
+    """Kernels launched by liblens_b200.so since it was loaded."""
+    n = C.c_int64(0)
+    check(lib().lens_launch_count(C.byref(n)), "lens_launch_count")
+    return int(n.value)

@@ -1,6 +1,8 @@
 // Diagnostics entry points of the C ABI.
 #include "common.cuh"
 
+#include <atomic>
+
 namespace lens {
 
 static thread_local char g_err[512] = "";
@@ -14,6 +16,10 @@ void set_err(const char *fmt, ...)
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launches() { return g_launches.load(std::memory_order_relaxed); }
 
 int sm_count()
 {
@@ -43,5 +49,13 @@ extern "C" int lens_device_sm_count(int *n_sm)
         return (int)cudaErrorNoDevice;
     }
     *n_sm = n;
+    return 0;
+}
+
+namespace lens { long long launches(); }
+extern "C" int lens_launch_count(int64_t *n_launches)
+{
+    LENS_CHECK_ARG(n_launches != nullptr, "lens_launch_count: NULL argument");
+    *n_launches = lens::launches();
     return 0;
 }

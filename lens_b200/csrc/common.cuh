@@ -31,7 +31,13 @@ void set_err(const char *fmt, ...);
         }                                                                            \
     } while (0)
 
-#define LENS_LAUNCH_CHECK() LENS_CUDA(cudaGetLastError())
+// every kernel launch of the library goes through this (counts launches, surfaces launch errors)
+void count_launch();
+#define LENS_LAUNCH_CHECK()          \
+    do {                             \
+        ::lens::count_launch();      \
+        LENS_CUDA(cudaGetLastError()); \
+    } while (0)
 
 static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 

@@ -300,6 +300,7 @@ static int launch_feature(SnnHandle *h, const uint8_t *pooled, const float *xin,
     int threads = (std::max(std::max(h->I, h->Fp), 32) + 31) & ~31;
     int Ipad = (h->I + 31) & ~31;
     size_t smem = (size_t)kChunk * Ipad * 4 + kChunk * sizeof(int);
+    LaunchTimer timer(h, st, 0);
     feature_kernel<<<nb, threads, smem, st>>>(p);
     LENS_LAUNCH_CHECK();
     return 0;
@@ -315,6 +316,7 @@ static int launch_output_simt(SnnHandle *h, int b0, int nb, int steps, float *co
     p.counts = counts; p.spikes_out = spikes_out; p.out_steps = out_steps;
     size_t smem = (size_t)kChunk * h->Fp * 4 + kChunk * sizeof(int);
     dim3 grid(nb, ceil_div(h->P, kOutThreads));
+    LaunchTimer timer(h, st, 1);
     output_simt_kernel<<<grid, kOutThreads, smem, st>>>(p);
     LENS_LAUNCH_CHECK();
     return 0;
@@ -494,4 +496,34 @@ extern "C" int lens_snn_forward_float(void *handle, const float *x, int B, int s
     LENS_CHECK_ARG(x && spikes_out, "lens_snn_forward_float: NULL buffer");
     return forward_common(h, nullptr, x, B, steps, nullptr, spikes_out, nullptr, nullptr,
                           LENS_SNN_SIMT, as_stream(stream));
+}
+
+extern "C" int lens_snn_set_timing(void *handle, int enable)
+{
+    LENS_CHECK_ARG(handle, "lens_snn_set_timing: NULL handle");
+    SnnHandle *h = static_cast<SnnHandle *>(handle);
+    h->timing = enable != 0;
+    return 0;
+}
+
+extern "C" int lens_snn_get_timing(void *handle, float *feature_ms, float *output_ms,
+                                   int64_t *n_feature, int64_t *n_output)
+{
+    LENS_CHECK_ARG(handle, "lens_snn_get_timing: NULL handle");
+    SnnHandle *h = static_cast<SnnHandle *>(handle);
+    float ms[2] = {0.f, 0.f};
+    int64_t n[2] = {0, 0};
+    for (auto &t : h->timed) {
+        LENS_CUDA(cudaEventSynchronize(t.stop));
+        float e = 0.f;
+        LENS_CUDA(cudaEventElapsedTime(&e, t.start, t.stop));
+        ms[t.kind] += e; n[t.kind] += 1;
+        cudaEventDestroy(t.start); cudaEventDestroy(t.stop);
+    }
+    h->timed.clear();
+    if (feature_ms) *feature_ms = ms[0];
+    if (output_ms) *output_ms = ms[1];
+    if (n_feature) *n_feature = n[0];
+    if (n_output) *n_output = n[1];
+    return 0;
 }

@@ -2,6 +2,8 @@
 #pragma once
 #include "common.cuh"
 
+#include <vector>
+
 namespace lens {
 
 // Fixed-point grid of a weight row: w = m * 2^q with |m| < 2^46 (see snn.cu).
@@ -29,6 +31,28 @@ struct SnnHandle {
     int8_t *Wo_planes = nullptr;  // [P_tiles][kPlanes][...] canonical UMMA layout
     int P_tiles = 0;
     int device = 0;
+    // optional per-kernel timing (lens_snn_set_timing)
+    struct TimedLaunch { cudaEvent_t start, stop; int kind; };   // kind 0 = feature, 1 = output
+    bool timing = false;
+    std::vector<TimedLaunch> timed;
+};
+
+// RAII bracket: records start/stop events around a launch when timing is enabled.
+struct LaunchTimer {
+    SnnHandle *h; cudaStream_t st; SnnHandle::TimedLaunch t; bool on;
+    LaunchTimer(SnnHandle *h_, cudaStream_t st_, int kind) : h(h_), st(st_), on(h_->timing)
+    {
+        if (!on) return;
+        t.kind = kind;
+        cudaEventCreate(&t.start); cudaEventCreate(&t.stop);
+        cudaEventRecord(t.start, st);
+    }
+    ~LaunchTimer()
+    {
+        if (!on) return;
+        cudaEventRecord(t.stop, st);
+        h->timed.push_back(t);
+    }
 };
 
 // snn_tc.cu

@@ -156,6 +156,17 @@ class B200Network:
               "lens_snn_get_state")
         return v0, v1, v2
 
+    def set_timing(self, enable=True):
+        check(_lib.lib().lens_snn_set_timing(self._h, int(enable)), "lens_snn_set_timing")
+
+    def get_timing(self):
+        """-> dict(feature_ms, output_ms, n_feature, n_output) accumulated since the last call."""
+        f, o = C.c_float(0), C.c_float(0)
+        nf, no = C.c_int64(0), C.c_int64(0)
+        check(_lib.lib().lens_snn_get_timing(self._h, C.byref(f), C.byref(o), C.byref(nf), C.byref(no)),
+              "lens_snn_get_timing")
+        return dict(feature_ms=f.value, output_ms=o.value, n_feature=nf.value, n_output=no.value)
+
     def overflow(self):
         o = torch.zeros((1,), dtype=torch.int64, device=self.device)
         check(_lib.lib().lens_snn_get_overflow(self._h, ptr(o), stream_ptr()), "lens_snn_get_overflow")

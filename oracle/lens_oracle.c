@@ -117,13 +117,14 @@ typedef struct {
     uint8_t *shift;/* [n_in][n_out] left shift relative to the row's smallest ulp exponent     */
     int64_t *w64;  /* [n_in][n_out] mant * 2^shift for rows that fit 64-bit accumulation, else 0 */
     int *emin;     /* [n_out] exponent of the row's smallest ulp: w = mant * 2^(emin+shift)    */
+    float *scale;  /* [n_out] 2^emin when that is a normal float, else 0 (-> ldexpf path)      */
     int *wide;     /* [n_out] 1 if the row needs the 128-bit accumulator                       */
     int any_wide, unsupported;
 } exact_layer;
 
 static void exact_layer_free(exact_layer *L)
 {
-    free(L->mant); free(L->shift); free(L->w64); free(L->emin); free(L->wide);
+    free(L->mant); free(L->shift); free(L->w64); free(L->emin); free(L->wide); free(L->scale);
     memset(L, 0, sizeof(*L));
 }
 
@@ -137,7 +138,8 @@ static int exact_layer_init(exact_layer *L, const float *w, int n_out, int n_in)
     L->w64 = (int64_t *)calloc((size_t)n_out * n_in, sizeof(int64_t));
     L->emin = (int *)calloc((size_t)n_out, sizeof(int));
     L->wide = (int *)calloc((size_t)n_out, sizeof(int));
-    if (!L->mant || !L->shift || !L->w64 || !L->emin || !L->wide) return -2;
+    L->scale = (float *)calloc((size_t)n_out, sizeof(float));
+    if (!L->scale || !L->mant || !L->shift || !L->w64 || !L->emin || !L->wide) return -2;
     for (int n = 0; n < n_out; ++n) {
         int lo = 1 << 30, hi = -(1 << 30);
         for (int kk = 0; kk < n_in; ++kk) {
@@ -150,6 +152,7 @@ static int exact_layer_init(exact_layer *L, const float *w, int n_out, int n_in)
         }
         if (hi < lo) { L->emin[n] = 0; continue; }        /* all-zero row */
         L->emin[n] = lo;
+        if (lo >= -126 && lo <= 127) L->scale[n] = ldexpf(1.0f, lo);   /* exact power of two */
         int span = hi - lo;                                /* bits needed for the largest |w| */
         /* s <= 127 (7 bits), n_in terms (<= 2^16) -> headroom 23 bits */
         if (span + 23 > 62) { L->wide[n] = 1; L->any_wide = 1; }
@@ -290,7 +293,9 @@ static void exact_contract(const exact_layer *L, const int *idx, const int *cnt,
     }
     for (int n = 0; n < n_out; ++n) {
         if (L->any_wide && L->wide[n]) x[n] = i128_to_f32(acc128[n], L->emin[n]);
-        else x[n] = ldexpf((float)acc64[n], L->emin[n]); /* int64 -> f32 is one RNE rounding */
+        else if (L->scale[n] != 0.0f) x[n] = (float)acc64[n] * L->scale[n]; /* int64 -> f32: one RNE
+                                                    rounding; the power-of-two scaling is exact   */
+        else x[n] = ldexpf((float)acc64[n], L->emin[n]);
     }
 }
 

@@ -37,20 +37,10 @@ def golden():
 
 
 def synth_weights(I, F, P, seed):
-    """Random weights with the statistics of the trained LENS models."""
-    rng = np.random.default_rng(seed)
-    kind = rng.random((F, I))
-    Wf = np.where(kind < 0.30, rng.exponential(0.147, (F, I)),
-                  np.where(kind < 0.83, -rng.exponential(0.089, (F, I)), 0.0))
-    Wf = np.clip(Wf, -4.7, 1.05).astype(np.float32)
-    Wo = np.clip(rng.normal(0.0, 0.0143, (P, F)), -0.11, 0.055)
-    Wo = np.where(np.abs(Wo) < 1e-6, 1e-6, Wo).astype(np.float32)
-    return Wf, Wo
+    from lens_b200 import synth
+    return synth.weights(I, F, P, seed)
 
 
 def synth_pooled(B, Q, I, seed):
-    """Pooled pixel counts: geometric with mean ~8, ~43 % zeros, wrapped to u8."""
-    rng = np.random.default_rng(seed)
-    v = rng.geometric(1.0 / 15.0, (B, Q, I)) - 1
-    v = np.where(rng.random((B, Q, I)) < 0.40, 0, v)
-    return (v % 256).astype(np.uint8)
+    from lens_b200 import synth
+    return synth.pixel_counts((B, Q, I), seed)
