@@ -112,7 +112,26 @@ __device__ __forceinline__ int warp_compact(const uint8_t *row, int n, uint16_t 
     return base;
 }
 
-constexpr int kChunk = 16;   // timesteps processed between block-wide synchronisations
+// Same, for a row (timestep n) of a hidden-spike tile in the canonical UMMA layout.
+__device__ __forceinline__ int warp_compact_tiled(const uint8_t *tile, int n, int F, uint16_t *idx, uint8_t *cnt)
+{
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    for (int i0 = 0; i0 < F; i0 += 32) {
+        int i = i0 + lane;
+        uint8_t v = (i < F) ? tile[s1_byte_in_tile(n, i)] : (uint8_t)0;
+        unsigned m = __ballot_sync(0xffffffffu, v != 0);
+        if (v) {
+            int pos = base + __popc(m & ((1u << lane) - 1));
+            idx[pos] = (uint16_t)i;
+            cnt[pos] = v;
+        }
+        base += __popc(m);
+    }
+    return base;
+}
+
+constexpr int kChunk = kTileSteps;   // timesteps per hidden-spike tile (= steps between block syncs)
 
 struct FeatureParams {
     int I, F, Fp, T;
@@ -124,7 +143,7 @@ struct FeatureParams {
     const float *xin;         // [B][steps][I]       (float mode), exactly one of the two
     int steps;                // per stream (= Q*T in raster mode)
     float *v0, *v1;           // state, already offset to the first stream of this launch
-    int8_t *S1;               // [nb][steps][Fp]
+    int8_t *S1;               // [nb][chunks][Fp/16][kTileSteps][16] (tiled, see snn.cuh)
     uint8_t *hidden_steps;    // nullable [nb][steps][F]
     int64_t *overflow;
 };
@@ -140,11 +159,13 @@ __global__ void __launch_bounds__(1024) feature_kernel(FeatureParams p)
     uint16_t *l_idx = reinterpret_cast<uint16_t *>(s0 + kChunk * Ipad);   // [kChunk][Ipad]
     uint8_t *l_cnt = reinterpret_cast<uint8_t *>(l_idx + kChunk * Ipad);  // [kChunk][Ipad]
     int *n_act = reinterpret_cast<int *>(l_cnt + kChunk * Ipad);          // [kChunk]
+    uint8_t *tile = reinterpret_cast<uint8_t *>(n_act + kChunk);          // [Fp * kChunk] S1 tile (16 B aligned)
 
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, nwarps = blockDim.x >> 5;
     const float thr = p.thr, vmin = p.vmin;
+    const int n_chunks = (p.steps + kChunk - 1) / kChunk;
     float v0 = (tid < I) ? p.v0[(size_t)b * I + tid] : 0.0f;
     float v1 = (tid < F) ? p.v1[(size_t)b * F + tid] : 0.0f;
     const float scale = (tid < F) ? p.Wf_scale[tid] : 0.0f;
@@ -191,15 +212,20 @@ __global__ void __launch_bounds__(1024) feature_kernel(FeatureParams p)
                 const float x = __fmul_rn(__ll2float_rn(acc), scale);
                 float s = iaf_step(v1, x, thr, vmin);
                 if (s > (float)LENS_MAX_SPIKE) { s = (float)LENS_MAX_SPIKE; ++n_over; }
-                const size_t row = (size_t)b * p.steps + t0 + c;
-                p.S1[row * p.Fp + tid] = (int8_t)s;
-                if (p.hidden_steps) p.hidden_steps[row * F + tid] = (uint8_t)s;
+                tile[s1_byte_in_tile(c, tid)] = (uint8_t)s;
+                if (p.hidden_steps) p.hidden_steps[((size_t)b * p.steps + t0 + c) * F + tid] = (uint8_t)s;
             }
-        } else if (tid < p.Fp) {   // zero the K padding once per row
-            for (int c = 0; c < nc; ++c)
-                p.S1[((size_t)b * p.steps + t0 + c) * p.Fp + tid] = 0;
+            for (int c = nc; c < kChunk; ++c) tile[s1_byte_in_tile(c, tid)] = 0;   // ragged last tile
+        } else if (tid < p.Fp) {   // K padding
+            for (int c = 0; c < kChunk; ++c) tile[s1_byte_in_tile(c, tid)] = 0;
         }
         __syncthreads();
+        {   // the finished tile leaves with 16-byte stores
+            uint4 *dst = reinterpret_cast<uint4 *>(p.S1 + ((size_t)b * n_chunks + t0 / kChunk) * s1_tile_bytes(p.Fp));
+            const uint4 *src = reinterpret_cast<const uint4 *>(tile);
+            const int n16 = (int)(s1_tile_bytes(p.Fp) / 16);
+            for (int i = tid; i < n16; i += blockDim.x) dst[i] = src[i];
+        }
     }
     if (tid < I) p.v0[(size_t)b * I + tid] = v0;
     if (tid < F) p.v1[(size_t)b * F + tid] = v1;
@@ -211,7 +237,7 @@ struct OutputParams {
     float thr, vmin;
     const int64_t *Wo_fx;    // [F][P]
     const float *Wo_scale;   // [P]
-    const int8_t *S1;        // [nb][steps][Fp]
+    const int8_t *S1;        // [nb][chunks][Fp/16][kTileSteps][16] (tiled)
     int steps;
     float *v2;               // state, offset to first stream of the launch
     float *counts;           // [nb][steps/T][P], nullable
@@ -242,19 +268,20 @@ __global__ void __launch_bounds__(kOutThreads) output_simt_kernel(OutputParams p
     const int64_t *wcol = p.Wo_fx + (live ? place : 0);
     float count = 0.0f;
     const int Q = p.steps / p.T;
+    const int n_chunks = (p.steps + kChunk - 1) / kChunk;
 
     for (int t0 = 0; t0 < p.steps; t0 += kChunk) {
         const int nc = min(kChunk, p.steps - t0);
-        // stage the chunk's hidden-spike rows (contiguous nc*Fp bytes) with 16-byte loads
+        // stage the hidden-spike tile (kChunk * Fp contiguous bytes) with 16-byte loads
         {
-            const uint4 *src = reinterpret_cast<const uint4 *>(p.S1 + ((size_t)b * p.steps + t0) * Fp);
+            const uint4 *src = reinterpret_cast<const uint4 *>(p.S1 + ((size_t)b * n_chunks + t0 / kChunk) * s1_tile_bytes(Fp));
             uint4 *dst = reinterpret_cast<uint4 *>(s1);
-            const int n16 = nc * Fp / 16;
+            const int n16 = (int)(s1_tile_bytes(Fp) / 16);
             for (int i = tid; i < n16; i += kOutThreads) dst[i] = __ldg(src + i);
         }
         __syncthreads();
         for (int c = warp; c < nc; c += kOutThreads / 32) {
-            int n = warp_compact(s1 + c * Fp, F, l_idx + c * Fp, l_cnt + c * Fp);
+            int n = warp_compact_tiled(s1, c, F, l_idx + c * Fp, l_cnt + c * Fp);
             if ((tid & 31) == 0) n_act[c] = n;
         }
         __syncthreads();
@@ -299,7 +326,7 @@ static int launch_feature(SnnHandle *h, const uint8_t *pooled, const float *xin,
     p.S1 = h->S1; p.hidden_steps = hidden_steps; p.overflow = h->counters;
     int threads = (std::max(std::max(h->I, h->Fp), 32) + 31) & ~31;
     int Ipad = (h->I + 31) & ~31;
-    size_t smem = (size_t)kChunk * Ipad * 4 + kChunk * sizeof(int);
+    size_t smem = (size_t)kChunk * Ipad * 4 + kChunk * sizeof(int) + s1_tile_bytes(h->Fp);
     LaunchTimer timer(h, st, 0);
     feature_kernel<<<nb, threads, smem, st>>>(p);
     LENS_LAUNCH_CHECK();
@@ -339,7 +366,7 @@ static int forward_common(SnnHandle *h, const uint8_t *pooled, const float *xin,
                           float *counts, float *spikes_out, uint8_t *hidden_steps,
                           uint8_t *out_steps, int mode, cudaStream_t st)
 {
-    const size_t per_stream = (size_t)steps * h->Fp;
+    const size_t per_stream = (size_t)ceil_div(steps, kTileSteps) * s1_tile_bytes(h->Fp);
     int group = (int)std::min<size_t>((size_t)B, std::max<size_t>((size_t)1, scratch_budget() / std::max<size_t>(per_stream, 1)));
     int rc = ensure_scratch(h, per_stream * group);
     if (rc) return rc;

@@ -11,6 +11,14 @@ constexpr int kFxBits = 46;
 // Hidden-spike rows are stored as int8 padded to a multiple of 32 columns
 // (16-byte loads, and the K granularity of tcgen05 kind::i8).
 constexpr int kHiddenPad = 32;
+// Hidden spikes are exchanged between the feature and output kernels as tiles of kTileSteps
+// consecutive timesteps of one stream, stored in the canonical no-swizzle K-major UMMA layout
+//   S1[stream][chunk][kc = k / 16][n = step % kTileSteps][k % 16]      (int8)
+// i.e. a tile is kTileSteps * Fp contiguous bytes that one cp.async.bulk drops into shared memory
+// ready to be a tcgen05.mma B operand.
+constexpr int kTileSteps = 32;
+__host__ __device__ inline size_t s1_tile_bytes(int Fp) { return (size_t)kTileSteps * Fp; }
+__host__ __device__ inline int s1_byte_in_tile(int n, int k) { return (k >> 4) * (kTileSteps * 16) + n * 16 + (k & 15); }
 // Number of radix-256 balanced digits that cover the 47-bit signed fixed-point weights.
 constexpr int kPlanes = 6;
 

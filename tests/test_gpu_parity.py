@@ -106,7 +106,7 @@ def assert_same(res, ov, gv):
         assert np.array_equal(a, b), "membrane potentials differ"
 
 
-@pytest.mark.parametrize("mode", [1])
+@pytest.mark.parametrize("mode", [1, 2])
 def test_snn_config1_golden(golden, mode):
     """Bundled model + data: GPU == oracle bit for bit, and == the reference's own output."""
     g = golden("config1")
@@ -120,7 +120,7 @@ def test_snn_config1_golden(golden, mode):
     assert np.abs(gv[2][0] - g["v2"]).max() < 1e-5 and np.abs(gv[1][0] - g["v1"]).max() < 1e-5
 
 
-@pytest.mark.parametrize("mode", [1])
+@pytest.mark.parametrize("mode", [1, 2])
 def test_snn_brisevent_golden_prefix(golden, mode):
     """Second bundled model (k = 1, P = 641, multi-spike outputs): first 60 queries."""
     g = golden("brisevent")
@@ -141,7 +141,7 @@ def test_snn_brisevent_golden_prefix(golden, mode):
     (4, 40, 130, 33, 5, 2, 1),        # ragged: P not a multiple of the place tile, T odd
     (3, 9, 5, 7, 1, 1, 1),            # tiny
 ])
-@pytest.mark.parametrize("mode", [1])
+@pytest.mark.parametrize("mode", [1, 2])
 def test_snn_synthetic(I_dims, F, P, T, B, Q, calls, mode):
     I = I_dims * I_dims
     Wf, Wo = synth_weights(I, F, P, seed=F + P)
