@@ -119,7 +119,7 @@ __device__ __forceinline__ int warp_compact_tiled(const uint8_t *tile, int n, in
     int base = 0;
     for (int i0 = 0; i0 < F; i0 += 32) {
         int i = i0 + lane;
-        uint8_t v = (i < F) ? tile[s1_byte_in_tile(n, i)] : (uint8_t)0;
+        uint8_t v = (i < F) ? tile[s1_byte_in_half(n, i)] : (uint8_t)0;
         unsigned m = __ballot_sync(0xffffffffu, v != 0);
         if (v) {
             int pos = base + __popc(m & ((1u << lane) - 1));
@@ -143,7 +143,7 @@ struct FeatureParams {
     const float *xin;         // [B][steps][I]       (float mode), exactly one of the two
     int steps;                // per stream (= Q*T in raster mode)
     float *v0, *v1;           // state, already offset to the first stream of this launch
-    int8_t *S1;               // [nb][chunks][Fp/16][kTileSteps][16] (tiled, see snn.cuh)
+    int8_t *S1;               // [pairs][chunks][Fp/16][2*kTileSteps][16] (pair tiles, see snn.cuh)
     uint8_t *hidden_steps;    // nullable [nb][steps][F]
     int64_t *overflow;
 };
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(1024) feature_kernel(FeatureParams p)
     uint16_t *l_idx = reinterpret_cast<uint16_t *>(s0 + kChunk * Ipad);   // [kChunk][Ipad]
     uint8_t *l_cnt = reinterpret_cast<uint8_t *>(l_idx + kChunk * Ipad);  // [kChunk][Ipad]
     int *n_act = reinterpret_cast<int *>(l_cnt + kChunk * Ipad);          // [kChunk]
-    uint8_t *tile = reinterpret_cast<uint8_t *>(n_act + kChunk);          // [Fp * kChunk] S1 tile (16 B aligned)
+    uint8_t *tile = reinterpret_cast<uint8_t *>(n_act + kChunk);          // [Fp/16][kChunk][16] this stream's half tile
 
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
@@ -212,19 +212,21 @@ __global__ void __launch_bounds__(1024) feature_kernel(FeatureParams p)
                 const float x = __fmul_rn(__ll2float_rn(acc), scale);
                 float s = iaf_step(v1, x, thr, vmin);
                 if (s > (float)LENS_MAX_SPIKE) { s = (float)LENS_MAX_SPIKE; ++n_over; }
-                tile[s1_byte_in_tile(c, tid)] = (uint8_t)s;
+                tile[s1_byte_in_half(c, tid)] = (uint8_t)s;
                 if (p.hidden_steps) p.hidden_steps[((size_t)b * p.steps + t0 + c) * F + tid] = (uint8_t)s;
             }
-            for (int c = nc; c < kChunk; ++c) tile[s1_byte_in_tile(c, tid)] = 0;   // ragged last tile
+            for (int c = nc; c < kChunk; ++c) tile[s1_byte_in_half(c, tid)] = 0;   // ragged last tile
         } else if (tid < p.Fp) {   // K padding
-            for (int c = 0; c < kChunk; ++c) tile[s1_byte_in_tile(c, tid)] = 0;
+            for (int c = 0; c < kChunk; ++c) tile[s1_byte_in_half(c, tid)] = 0;
         }
         __syncthreads();
-        {   // the finished tile leaves with 16-byte stores
-            uint4 *dst = reinterpret_cast<uint4 *>(p.S1 + ((size_t)b * n_chunks + t0 / kChunk) * s1_tile_bytes(p.Fp));
+        {   // the finished half tile leaves with 16-byte stores into its rows of the pair tile
+            uint4 *dst = reinterpret_cast<uint4 *>(p.S1 + ((size_t)(b >> 1) * n_chunks + t0 / kChunk) * s1_tile_bytes(p.Fp));
             const uint4 *src = reinterpret_cast<const uint4 *>(tile);
-            const int n16 = (int)(s1_tile_bytes(p.Fp) / 16);
-            for (int i = tid; i < n16; i += blockDim.x) dst[i] = src[i];
+            const int n16 = p.Fp / 16 * kChunk;
+            const int sp = b & 1;
+            for (int i = tid; i < n16; i += blockDim.x)
+                dst[(i / kChunk) * kTileRows + sp * kChunk + (i % kChunk)] = src[i];
         }
     }
     if (tid < I) p.v0[(size_t)b * I + tid] = v0;
@@ -232,12 +234,187 @@ __global__ void __launch_bounds__(1024) feature_kernel(FeatureParams p)
     if (n_over) atomicAdd((unsigned long long *)p.overflow, (unsigned long long)n_over);
 }
 
+// --------------------------------------------------------------------------------
+// raster fast path of the feature layer
+// --------------------------------------------------------------------------------
+// lens/src/dataset.py:23,121: spike = (U[t][i] < pixel / 255).  pixel / 255 (fp32 division) is
+// monotone in the pixel value, so the comparison is equivalent to pixel > Uq[t][i] with
+//   Uq[t][i] = (smallest pixel in 1..255 with U[t][i] < pixel/255) - 1,   255 if there is none
+// -- one byte per (step, input), built once per handle by exact evaluation of the same fp32 division.
+__global__ void raster_thresholds_kernel(const float *__restrict__ U, int n, uint8_t *__restrict__ Uq)
+{
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const float u = U[idx];
+    int lo = 1, hi = 256;                       // first pixel value that spikes, 256 = never
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (u < __fdiv_rn((float)mid, 255.0f)) hi = mid;
+        else lo = mid + 1;
+    }
+    Uq[idx] = (uint8_t)(lo - 1);
+}
+
+constexpr int kRasterSlots = 4;      // streams processed concurrently by one CTA
+constexpr int kMaskWords = 8;        // I <= 256 inputs as a bitmask per timestep
+
+struct RasterParams {
+    int I, F, Fp, T, Q, steps, nb;
+    float vmin;
+    const int64_t *Wf_fx;     // [I][F]
+    const float *Wf_scale;    // [F]
+    const uint8_t *Uq;        // [T][I]
+    const uint8_t *pooled;    // [nb][Q][I]
+    float *v1;                // [nb][F] (offset to the first stream of the launch)
+    int8_t *S1;               // pair tiles
+    uint8_t *hidden_steps;    // nullable [nb][steps][F]
+    int64_t *overflow;
+};
+
+// Feature layer for binary raster input, threshold 1, IAF#0 at rest (v0 == 0): IAF#0 is then the
+// identity (v = 0 + 1 -> one spike -> v = 0), so input spikes come straight from the byte
+// comparison above.  Persistent CTAs; each CTA keeps the whole fixed-point W_feat in shared
+// memory and runs kRasterSlots streams side by side (slot = blockDim.x / kRasterSlots threads,
+// thread f of a slot owns feature neuron f with its membrane potential in a register).
+// Per tile of 32 timesteps: (A) every warp builds input-spike bitmasks for some steps,
+// (C) every thread walks its 32 steps: exact int64 sum over the set bits, IAF#1, spike byte
+// into the slot's tile, (W) the tile leaves for HBM in the pair-tile layout.
+template <int kWords>
+__global__ void __launch_bounds__(1024, 1) feature_raster_kernel(RasterParams p)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int I = p.I, F = p.F, Fp = p.Fp;
+    const int slot_threads = blockDim.x / kRasterSlots;
+    const int slot = threadIdx.x / slot_threads;
+    const int f = threadIdx.x - slot * slot_threads;
+    const int lane = threadIdx.x & 31;
+    const int slot_warp = f >> 5, slot_warps = slot_threads >> 5;
+    int64_t *sW = reinterpret_cast<int64_t *>(smem_raw);                       // [I][F]
+    uint8_t *sUq = reinterpret_cast<uint8_t *>(sW + (size_t)I * F);            // [T][I]
+    size_t off = ((size_t)I * F * 8 + (size_t)p.T * I + 15) & ~(size_t)15;
+    uint32_t *sMask = reinterpret_cast<uint32_t *>(smem_raw + off) + slot * (kChunk * kWords);   // [kChunk][kWords]
+    off += (size_t)kRasterSlots * kChunk * kWords * 4;
+    uint8_t *tile = smem_raw + off + (size_t)slot * kChunk * Fp;               // [Fp/16][kChunk][16]
+
+    for (int i = threadIdx.x; i < I * F; i += blockDim.x) sW[i] = p.Wf_fx[i];
+    for (int i = threadIdx.x; i < p.T * I; i += blockDim.x) sUq[i] = p.Uq[i];
+    const float scale = (f < F) ? p.Wf_scale[f] : 0.0f;
+    const float vmin = p.vmin;
+    const int n_chunks = (p.steps + kChunk - 1) / kChunk;
+    int64_t n_over = 0;
+    __syncthreads();
+
+    const int n_groups = (p.nb + kRasterSlots - 1) / kRasterSlots;
+    for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        const int b = g * kRasterSlots + slot;
+        const bool live = b < p.nb;
+        float v1 = (live && f < F) ? p.v1[(size_t)b * F + f] : 0.0f;
+        for (int ch = 0; ch < n_chunks; ++ch) {
+            const int t0 = ch * kChunk;
+            const int nc = min(kChunk, p.steps - t0);
+            // ---- (A) input-spike bitmasks of this tile's steps
+            if (live) {
+                for (int c = slot_warp; c < nc; c += slot_warps) {
+                    const int step = t0 + c;
+                    const int q = step / p.T, t = step - q * p.T;
+                    const uint8_t *px = p.pooled + ((size_t)b * p.Q + q) * I;
+                    const uint8_t *uq = sUq + (size_t)t * I;
+#pragma unroll
+                    for (int w = 0; w < kWords; ++w) {
+                        const int i = w * 32 + lane;
+                        const bool spike = (i < I) && (__ldg(px + i) > uq[i]);
+                        const unsigned m = __ballot_sync(0xffffffffu, spike);
+                        if (lane == 0) sMask[c * kWords + w] = m;
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- (C) exact contraction over the set bits + IAF#1
+            if (live && f < F) {
+                for (int c = 0; c < nc; ++c) {
+                    int64_t acc = 0;
+#pragma unroll
+                    for (int w = 0; w < kWords; ++w) {
+                        unsigned m = sMask[c * kWords + w];
+                        while (m) {
+                            const int i = w * 32 + __ffs(m) - 1;
+                            m &= m - 1;
+                            acc += sW[i * F + f];
+                        }
+                    }
+                    const float x = __fmul_rn(__ll2float_rn(acc), scale);
+                    float vv = __fadd_rn(v1, x);                // IAF#1 with thr == 1 (see iaf_step)
+                    float s = (vv >= 1.0f) ? 1.0f : 0.0f;
+                    if (vv >= 2.0f) s = truncf(vv);
+                    vv = __fsub_rn(vv, s);
+                    v1 = __fadd_rn(fmaxf(__fsub_rn(vv, vmin), 0.0f), vmin);
+                    if (s > (float)LENS_MAX_SPIKE) { s = (float)LENS_MAX_SPIKE; ++n_over; }
+                    tile[s1_byte_in_half(c, f)] = (uint8_t)s;
+                    if (p.hidden_steps) p.hidden_steps[((size_t)b * p.steps + t0 + c) * F + f] = (uint8_t)s;
+                }
+                for (int c = nc; c < kChunk; ++c) tile[s1_byte_in_half(c, f)] = 0;   // ragged last tile
+            } else if (live && f < Fp) {
+                for (int c = 0; c < kChunk; ++c) tile[s1_byte_in_half(c, f)] = 0;    // K padding
+            }
+            __syncthreads();
+            // ---- (W) this stream's rows of the pair tile
+            if (live) {
+                uint4 *dst = reinterpret_cast<uint4 *>(p.S1 + ((size_t)(b >> 1) * n_chunks + ch) * s1_tile_bytes(Fp));
+                const uint4 *src = reinterpret_cast<const uint4 *>(tile);
+                const int n16 = Fp / 16 * kChunk;
+                const int sp = b & 1;
+                for (int i = f; i < n16; i += slot_threads)
+                    dst[(i / kChunk) * kTileRows + sp * kChunk + (i % kChunk)] = src[i];
+            }
+        }
+        if (live && f < F) p.v1[(size_t)b * F + f] = v1;
+    }
+    if (n_over) atomicAdd((unsigned long long *)p.overflow, (unsigned long long)n_over);
+}
+
+static size_t raster_smem_bytes(const SnnHandle *h, int words)
+{
+    size_t off = ((size_t)h->I * h->F * 8 + (size_t)h->T * h->I + 15) & ~(size_t)15;
+    return off + (size_t)kRasterSlots * kChunk * words * 4 + (size_t)kRasterSlots * kChunk * h->Fp;
+}
+
+static int raster_words(const SnnHandle *h) { return h->I <= 128 ? 4 : 8; }
+
+static bool raster_path_ok(const SnnHandle *h)
+{
+    return h->Uq && h->thr == 1.0f && !h->v0_dirty && h->I <= 32 * kMaskWords &&
+           h->Fp * kRasterSlots <= 1024 && raster_smem_bytes(h, raster_words(h)) <= 227 * 1024;
+}
+
+static int launch_feature_raster(SnnHandle *h, const uint8_t *pooled, int b0, int nb, int steps,
+                                 uint8_t *hidden_steps, cudaStream_t st)
+{
+    RasterParams p;
+    p.I = h->I; p.F = h->F; p.Fp = h->Fp; p.T = h->T; p.Q = steps / h->T; p.steps = steps; p.nb = nb;
+    p.vmin = h->vmin; p.Wf_fx = h->Wf_fx; p.Wf_scale = h->Wf_scale; p.Uq = h->Uq; p.pooled = pooled;
+    p.v1 = h->v1 + (size_t)b0 * h->F; p.S1 = h->S1; p.hidden_steps = hidden_steps; p.overflow = h->counters;
+    const int words = raster_words(h);
+    const size_t smem = raster_smem_bytes(h, words);
+    const int threads = kRasterSlots * h->Fp;
+    const int grid = std::min(std::max(sm_count(), 1), ceil_div(nb, kRasterSlots));
+    LaunchTimer timer(h, st, 0);
+    if (words == 4) {
+        LENS_CUDA(cudaFuncSetAttribute(feature_raster_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        feature_raster_kernel<4><<<grid, threads, smem, st>>>(p);
+    } else {
+        LENS_CUDA(cudaFuncSetAttribute(feature_raster_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        feature_raster_kernel<8><<<grid, threads, smem, st>>>(p);
+    }
+    LENS_LAUNCH_CHECK();
+    return 0;
+}
+
 struct OutputParams {
     int F, Fp, P, T;
     float thr, vmin;
     const int64_t *Wo_fx;    // [F][P]
     const float *Wo_scale;   // [P]
-    const int8_t *S1;        // [nb][chunks][Fp/16][kTileSteps][16] (tiled)
+    const int8_t *S1;        // [pairs][chunks][Fp/16][2*kTileSteps][16] (pair tiles)
     int steps;
     float *v2;               // state, offset to first stream of the launch
     float *counts;           // [nb][steps/T][P], nullable
@@ -272,12 +449,14 @@ __global__ void __launch_bounds__(kOutThreads) output_simt_kernel(OutputParams p
 
     for (int t0 = 0; t0 < p.steps; t0 += kChunk) {
         const int nc = min(kChunk, p.steps - t0);
-        // stage the hidden-spike tile (kChunk * Fp contiguous bytes) with 16-byte loads
+        // stage this stream's rows of the pair tile with 16-byte loads
         {
-            const uint4 *src = reinterpret_cast<const uint4 *>(p.S1 + ((size_t)b * n_chunks + t0 / kChunk) * s1_tile_bytes(Fp));
+            const uint4 *src = reinterpret_cast<const uint4 *>(p.S1 + ((size_t)(b >> 1) * n_chunks + t0 / kChunk) * s1_tile_bytes(Fp));
             uint4 *dst = reinterpret_cast<uint4 *>(s1);
-            const int n16 = (int)(s1_tile_bytes(Fp) / 16);
-            for (int i = tid; i < n16; i += kOutThreads) dst[i] = __ldg(src + i);
+            const int n16 = Fp / 16 * kChunk;
+            const int sp = b & 1;
+            for (int i = tid; i < n16; i += kOutThreads)
+                dst[i] = __ldg(src + (i / kChunk) * kTileRows + sp * kChunk + (i % kChunk));
         }
         __syncthreads();
         for (int c = warp; c < nc; c += kOutThreads / 32) {
@@ -326,7 +505,7 @@ static int launch_feature(SnnHandle *h, const uint8_t *pooled, const float *xin,
     p.S1 = h->S1; p.hidden_steps = hidden_steps; p.overflow = h->counters;
     int threads = (std::max(std::max(h->I, h->Fp), 32) + 31) & ~31;
     int Ipad = (h->I + 31) & ~31;
-    size_t smem = (size_t)kChunk * Ipad * 4 + kChunk * sizeof(int) + s1_tile_bytes(h->Fp);
+    size_t smem = (size_t)kChunk * Ipad * 4 + kChunk * sizeof(int) + (size_t)kChunk * h->Fp;
     LaunchTimer timer(h, st, 0);
     feature_kernel<<<nb, threads, smem, st>>>(p);
     LENS_LAUNCH_CHECK();
@@ -366,9 +545,10 @@ static int forward_common(SnnHandle *h, const uint8_t *pooled, const float *xin,
                           float *counts, float *spikes_out, uint8_t *hidden_steps,
                           uint8_t *out_steps, int mode, cudaStream_t st)
 {
-    const size_t per_stream = (size_t)ceil_div(steps, kTileSteps) * s1_tile_bytes(h->Fp);
-    int group = (int)std::min<size_t>((size_t)B, std::max<size_t>((size_t)1, scratch_budget() / std::max<size_t>(per_stream, 1)));
-    int rc = ensure_scratch(h, per_stream * group);
+    const size_t per_pair = (size_t)ceil_div(steps, kTileSteps) * s1_tile_bytes(h->Fp);
+    // streams are processed in groups (even size: a pair tile never straddles two groups)
+    int group = (int)std::min<size_t>((size_t)B + (B & 1), 2 * std::max<size_t>((size_t)1, scratch_budget() / std::max<size_t>(per_pair, 1)));
+    int rc = ensure_scratch(h, per_pair * (group / 2));
     if (rc) return rc;
     const int Q = steps / h->T;
     bool use_tc = false;
@@ -382,9 +562,12 @@ static int forward_common(SnnHandle *h, const uint8_t *pooled, const float *xin,
     }
     for (int b0 = 0; b0 < B; b0 += group) {
         const int nb = std::min(group, B - b0);
-        rc = launch_feature(h, pooled ? pooled + (size_t)b0 * Q * h->I : nullptr,
-                            xin ? xin + (size_t)b0 * steps * h->I : nullptr, b0, nb, steps,
-                            hidden_steps ? hidden_steps + (size_t)b0 * steps * h->F : nullptr, st);
+        uint8_t *hs = hidden_steps ? hidden_steps + (size_t)b0 * steps * h->F : nullptr;
+        if (pooled && raster_path_ok(h))
+            rc = launch_feature_raster(h, pooled + (size_t)b0 * Q * h->I, b0, nb, steps, hs, st);
+        else
+            rc = launch_feature(h, pooled ? pooled + (size_t)b0 * Q * h->I : nullptr,
+                                xin ? xin + (size_t)b0 * steps * h->I : nullptr, b0, nb, steps, hs, st);
         if (rc) return rc;
         float *c = counts ? counts + (size_t)b0 * Q * h->P : nullptr;
         uint8_t *os = out_steps ? out_steps + (size_t)b0 * steps * h->P : nullptr;
@@ -435,6 +618,10 @@ extern "C" int lens_snn_create(int I, int F, int P, int T, float thr, float v_mi
     if (U) {
         H_CUDA(cudaMalloc(&h->U, (size_t)T * I * sizeof(float)));
         H_CUDA(cudaMemcpyAsync(h->U, U, (size_t)T * I * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        H_CUDA(cudaMalloc(&h->Uq, (size_t)T * I));
+        raster_thresholds_kernel<<<ceil_div(T * I, 256), 256, 0, st>>>(h->U, T * I, h->Uq);
+        count_launch();
+        H_CUDA(cudaGetLastError());
     }
     H_CUDA(cudaMalloc(&h->v0, (size_t)max_streams * I * sizeof(float)));
     H_CUDA(cudaMalloc(&h->v1, (size_t)max_streams * F * sizeof(float)));
@@ -461,7 +648,7 @@ extern "C" int lens_snn_destroy(void *handle)
     SnnHandle *h = static_cast<SnnHandle *>(handle);
     snn_tc_release(h);
     cudaFree(h->Wf_fx); cudaFree(h->Wf_scale); cudaFree(h->Wo_fx); cudaFree(h->Wo_scale);
-    cudaFree(h->U); cudaFree(h->v0); cudaFree(h->v1); cudaFree(h->v2);
+    cudaFree(h->U); cudaFree(h->Uq); cudaFree(h->v0); cudaFree(h->v1); cudaFree(h->v2);
     cudaFree(h->counters); cudaFree(h->S1);
     delete h;
     return 0;
@@ -476,6 +663,7 @@ extern "C" int lens_snn_reset(void *handle, void *stream)
     LENS_CUDA(cudaMemsetAsync(h->v1, 0, (size_t)h->maxB * h->F * sizeof(float), st));
     LENS_CUDA(cudaMemsetAsync(h->v2, 0, (size_t)h->maxB * h->P * sizeof(float), st));
     LENS_CUDA(cudaMemsetAsync(h->counters, 0, sizeof(int64_t), st));
+    h->v0_dirty = false;
     return 0;
 }
 
@@ -521,6 +709,7 @@ extern "C" int lens_snn_forward_float(void *handle, const float *x, int B, int s
     LENS_CHECK_ARG(B >= 0 && steps >= 0 && B <= h->maxB, "lens_snn_forward_float: B=%d exceeds max_streams=%d", B, h->maxB);
     if (B == 0 || steps == 0) return 0;
     LENS_CHECK_ARG(x && spikes_out, "lens_snn_forward_float: NULL buffer");
+    h->v0_dirty = true;   // arbitrary float input can leave IAF#0 away from rest
     return forward_common(h, nullptr, x, B, steps, nullptr, spikes_out, nullptr, nullptr,
                           LENS_SNN_SIMT, as_stream(stream));
 }

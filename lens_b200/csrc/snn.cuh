@@ -11,14 +11,22 @@ constexpr int kFxBits = 46;
 // Hidden-spike rows are stored as int8 padded to a multiple of 32 columns
 // (16-byte loads, and the K granularity of tcgen05 kind::i8).
 constexpr int kHiddenPad = 32;
-// Hidden spikes are exchanged between the feature and output kernels as tiles of kTileSteps
-// consecutive timesteps of one stream, stored in the canonical no-swizzle K-major UMMA layout
-//   S1[stream][chunk][kc = k / 16][n = step % kTileSteps][k % 16]      (int8)
-// i.e. a tile is kTileSteps * Fp contiguous bytes that one cp.async.bulk drops into shared memory
-// ready to be a tcgen05.mma B operand.
+// Hidden spikes are exchanged between the feature and output kernels as tiles covering
+// kTileSteps consecutive timesteps of a PAIR of streams (2b, 2b+1), stored in the canonical
+// no-swizzle K-major UMMA layout
+//   S1[pair][chunk][kc = k / 16][row = (stream & 1) * kTileSteps + step % kTileSteps][k % 16]   (int8)
+// i.e. a tile is 2 * kTileSteps * Fp contiguous bytes that one cp.async.bulk drops into shared
+// memory ready to be the N = 64 B operand of tcgen05.mma (columns 0..31 = even stream, 32..63 = odd).
 constexpr int kTileSteps = 32;
-__host__ __device__ inline size_t s1_tile_bytes(int Fp) { return (size_t)kTileSteps * Fp; }
-__host__ __device__ inline int s1_byte_in_tile(int n, int k) { return (k >> 4) * (kTileSteps * 16) + n * 16 + (k & 15); }
+constexpr int kTileRows = 2 * kTileSteps;
+__host__ __device__ inline size_t s1_tile_bytes(int Fp) { return (size_t)kTileRows * Fp; }
+// byte offset of (step n of stream-in-pair sp, hidden unit k) inside a pair tile
+__host__ __device__ inline int s1_byte_in_tile(int sp, int n, int k)
+{
+    return (k >> 4) * (kTileRows * 16) + (sp * kTileSteps + n) * 16 + (k & 15);
+}
+// byte offset inside a single-stream staging tile [kc][kTileSteps][16]
+__host__ __device__ inline int s1_byte_in_half(int n, int k) { return (k >> 4) * (kTileSteps * 16) + n * 16 + (k & 15); }
 // Number of radix-256 balanced digits that cover the 47-bit signed fixed-point weights.
 constexpr int kPlanes = 6;
 
@@ -31,6 +39,8 @@ struct SnnHandle {
     int64_t *Wo_fx = nullptr;   // [F][P]  output weights, hidden-major, fixed point
     float *Wo_scale = nullptr;  // [P]     2^q per place
     float *U = nullptr;         // [T][I]  raster uniforms (nullable)
+    uint8_t *Uq = nullptr;      // [T][I]  raster thresholds: input i spikes at step t iff pixel > Uq[t][i]
+    bool v0_dirty = false;      // IAF#0 state may be non-zero (float path used): raster fast path is off
     float *v0 = nullptr, *v1 = nullptr, *v2 = nullptr;  // membrane potentials [maxB][I|F|P]
     int64_t *counters = nullptr;  // [0] spike overflow, [1] inexact weights
     int8_t *S1 = nullptr;         // scratch hidden spikes [streams][steps][Fp]

@@ -11,16 +11,20 @@
 // and the epilogue recombines X = sum_j P_j 256^j in int64, rounds ONCE to fp32 (cvt.rn.f32.s64)
 // and scales by the row's 2^q: bit-identical to the event-driven kernel and to the CPU oracle.
 //
-// Mapping: M = 128 places (TMEM lanes), N = 32 consecutive timesteps of one stream (TMEM columns),
-// K = F padded to 32.  Time runs along the columns, so each epilogue thread owns one place and scans
-// its 32 columns serially with the membrane potential and spike count in registers -- the recurrence
-// never leaves the register file for a whole stream.  A CTA owns one place tile for the whole
-// launch: its 6 digit planes (6 x 128 x Fp bytes, canonical no-swizzle K-major core-matrix layout)
-// stay resident in shared memory; hidden-spike tiles (32 x Fp bytes, written by feature_kernel
-// directly in the canonical layout) stream in through a 4-stage cp.async.bulk (TMA) ring; two
-// 6 x 32-column int32 accumulator sets in TMEM ping-pong between the MMA warp and the 4 epilogue warps.
+// Mapping: M = 128 places (TMEM lanes), N = 64 columns = 32 consecutive timesteps of TWO streams
+// (columns 0..31 even stream, 32..63 odd stream), K = F padded to 32.  Time runs along the columns,
+// so an epilogue thread owns one (place, stream) and scans its 32 columns serially with the membrane
+// potential and spike count in registers -- the recurrence never leaves the register file for a
+// whole stream.  A CTA owns one place tile for the whole launch: its 6 digit planes (6 x 128 x Fp
+// bytes, canonical no-swizzle K-major core-matrix layout) stay resident in shared memory; hidden-
+// spike pair tiles (64 x Fp bytes, written by feature_kernel directly in the canonical layout)
+// stream in through a cp.async.bulk (TMA) ring.  The 6 x 64-column int32 accumulator set lives in
+// TMEM; the two epilogue warpgroups (one per stream of the pair) drain it into registers as three
+// 16+16-bit partial sums per step (tcgen05.ld), hand it back to the MMA warp at once and do the
+// recombination + IAF arithmetic from registers while the next tile's MMAs run.
 //
-// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue of
+// the even stream, warps 6..9 = epilogue of the odd stream.
 #include "snn.cuh"
 
 #include <algorithm>
@@ -30,15 +34,28 @@ namespace lens {
 namespace tc {
 
 constexpr int kM = 128;                 // places per CTA tile
-constexpr int kN = kTileSteps;          // timesteps per MMA (TMEM columns per plane)
-constexpr int kStages = 4;              // hidden-spike tiles in flight
-constexpr int kAccBufs = 2;             // accumulator sets in TMEM
-constexpr int kTmemCols = 512;          // allocation (power of two >= kAccBufs * kPlanes * kN = 384)
-constexpr int kThreads = 192;
-
+constexpr int kN = kTileRows;           // TMEM columns per plane: 2 streams x 32 timesteps
+constexpr int kStages = 3;              // hidden-spike pair tiles in flight
+constexpr int kTmemCols = 512;          // allocation (power of two >= kPlanes * kN = 384)
+constexpr int kThreads = 320;
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
     return (uint32_t)__cvta_generic_to_shared(p);
+}
+// One lane of a fully converged warp (elect.sync): single-thread instructions (TMA, tcgen05.mma,
+// tcgen05.commit) are issued under this predicate from warp-uniform code so that their operands
+// stay in uniform registers.
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "elect.sync _|P1, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
@@ -106,6 +123,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int32_t (&r)[16])
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
 }
+// 32 consecutive 32-bit columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, int32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
+        "%14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, no-swizzle shared-memory operand descriptor (cute::UMMA::SmemDescriptor, version 1):
@@ -129,12 +158,12 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N)
 
 struct Params {
     const int8_t *planes;   // [P_tiles][kPlanes][Fp/16][128][16]
-    const int8_t *S1;       // [nb][chunks][Fp/16][32][16]
+    const int8_t *S1;       // [pairs][chunks][Fp/16][64][16]
     const float *scale;     // [P]
     float *v2;              // [nb][P] (offset to the first stream of the launch)
     float *counts;          // [nb][Q][P]
     uint8_t *out_steps;     // nullable [nb][steps][P]
-    int P, Fp, T, steps, chunks, nb, n_groups;
+    int P, Fp, T, steps, chunks, nb, n_pairs, n_groups;
     float thr, vmin;
 };
 
@@ -143,41 +172,47 @@ template <bool kUnitThr>
 __device__ __forceinline__ float iaf_out(float &v, float x, float thr, float vmin)
 {
     if (kUnitThr) {
+        // thr == 1: v / thr == v and s * thr == s exactly, so (v > 0) * trunc(v / thr) is
+        // 0 below 1, 1 in [1, 2) and trunc(v) above (rare: more than one spike in a step)
         float vv = __fadd_rn(v, x);
-        float s = (vv > 0.0f) ? truncf(vv) : 0.0f;     // v / 1.0f == v exactly
-        vv = __fsub_rn(vv, s);                         // s * 1.0f == s exactly
+        float s = (vv >= 1.0f) ? 1.0f : 0.0f;
+        if (vv >= 2.0f) s = truncf(vv);
+        vv = __fsub_rn(vv, s);
         v = __fadd_rn(fmaxf(__fsub_rn(vv, vmin), 0.0f), vmin);
         return s;
     }
     return iaf_step(v, x, thr, vmin);
 }
 
-template <bool kUnitThr>
+// kKSteps = Fp / 32 as a compile-time constant (0 = generic runtime loop): with it the 6 x kKSteps
+// MMAs of a tile are straight-line code whose descriptors are constant offsets from two uniform bases.
+template <bool kUnitThr, bool kDebug, int kKSteps>
 __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const int Fp = p.Fp;
-    const int ksteps = Fp / 32;
+    const int ksteps = kKSteps > 0 ? kKSteps : Fp / 32;
     const uint32_t plane_bytes = (uint32_t)kM * Fp;          // 128 rows x Fp bytes
-    const uint32_t tile_bytes = (uint32_t)kN * Fp;           // 32 steps x Fp bytes
+    const uint32_t tile_bytes = (uint32_t)kN * Fp;           // 64 rows x Fp bytes
     uint8_t *sA = smem;                                      // [kPlanes][plane_bytes]
     uint8_t *sB = sA + kPlanes * plane_bytes;                // [kStages][tile_bytes]
     uint64_t *bars = reinterpret_cast<uint64_t *>(sB + kStages * tile_bytes);
     uint64_t *a_full = bars;                                 // [1]
     uint64_t *b_full = bars + 1;                             // [kStages]
     uint64_t *b_empty = b_full + kStages;                    // [kStages]
-    uint64_t *acc_full = b_empty + kStages;                  // [kAccBufs]
-    uint64_t *acc_empty = acc_full + kAccBufs;               // [kAccBufs]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + kAccBufs);
+    uint64_t *acc_full = b_empty + kStages;                  // [1]
+    uint64_t *acc_empty = acc_full + 1;                      // [1]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x;          // place tile
-    const int group = blockIdx.y;         // stream group: streams group, group + n_groups, ...
+    const int group = blockIdx.y;         // stream-pair group: pairs group, group + n_groups, ...
 
     if (threadIdx.x == 0) {
         mbar_init(a_full, 1);
         for (int i = 0; i < kStages; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
-        for (int i = 0; i < kAccBufs; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4); }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, 8);          // one arrival per epilogue warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {   // TMEM allocation (whole warp), address lands in shared memory
@@ -192,104 +227,138 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
+        // ===================== TMA producer (warp-uniform, one elected lane issues) ==============
+        if (elect_one()) {
             mbar_expect_tx(a_full, kPlanes * plane_bytes);
             const int8_t *src = p.planes + (size_t)tile * kPlanes * plane_bytes;
             for (int j = 0; j < kPlanes; ++j)
                 bulk_g2s(sA + j * plane_bytes, src + (size_t)j * plane_bytes, plane_bytes, a_full);
-            uint32_t it = 0;
-            for (int b = group; b < p.nb; b += p.n_groups) {
-                const int8_t *sb = p.S1 + (size_t)b * p.chunks * tile_bytes;
-                for (int c = 0; c < p.chunks; ++c, ++it) {
-                    const uint32_t stage = it % kStages, phase = (it / kStages) & 1;
-                    mbar_wait(b_empty + stage, phase ^ 1);
+        }
+        __syncwarp();
+        uint32_t it = 0;
+        for (int pr = group; pr < p.n_pairs; pr += p.n_groups) {
+            const int8_t *sb = p.S1 + (size_t)pr * p.chunks * tile_bytes;
+            for (int c = 0; c < p.chunks; ++c, ++it) {
+                const uint32_t stage = it % kStages, phase = (it / kStages) & 1;
+                mbar_wait(b_empty + stage, phase ^ 1);
+                if (elect_one()) {
                     mbar_expect_tx(b_full + stage, tile_bytes);
                     bulk_g2s(sB + stage * tile_bytes, sb + (size_t)c * tile_bytes, tile_bytes, b_full + stage);
                 }
+                __syncwarp();
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc(kM, kN);
-            const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
-            mbar_wait(a_full, 0);
-            uint32_t it = 0;
-            for (int b = group; b < p.nb; b += p.n_groups) {
-                for (int c = 0; c < p.chunks; ++c, ++it) {
-                    const uint32_t stage = it % kStages, phase = (it / kStages) & 1;
-                    const uint32_t buf = it % kAccBufs, aphase = (it / kAccBufs) & 1;
-                    mbar_wait(acc_empty + buf, aphase ^ 1);     // epilogue drained this accumulator set
-                    mbar_wait(b_full + stage, phase);           // spikes landed
-                    tc_fence_after();
-                    for (int j = 0; j < kPlanes; ++j) {
-                        const uint32_t d = tmem_base + buf * (kPlanes * kN) + j * kN;
-                        for (int ks = 0; ks < ksteps; ++ks) {
-                            // K step = two 16-byte chunks: chunk stride = rows * 16 bytes
-                            const uint64_t da = make_desc(a_base + j * plane_bytes + ks * 2 * (kM * 16), kM * 16, 128);
-                            const uint64_t db = make_desc(b_base + stage * tile_bytes + ks * 2 * (kN * 16), kN * 16, 128);
-                            mma_i8(d, da, db, idesc, ks > 0 ? 1u : 0u);
+        // ===================== MMA issuer (warp-uniform, one elected lane issues) ================
+        const uint32_t idesc = make_idesc(kM, kN);
+        // descriptors differ only in the 14-bit start-address field: precompute, then add offsets
+        const uint64_t da0 = make_desc(smem_u32(sA), kM * 16, 128);
+        const uint64_t db0 = make_desc(smem_u32(sB), kN * 16, 128);
+        const uint32_t a_plane = plane_bytes >> 4, a_kstep = (2 * kM * 16) >> 4;
+        const uint32_t b_stage = tile_bytes >> 4, b_kstep = (2 * kN * 16) >> 4;
+        mbar_wait(a_full, 0);
+        uint32_t it = 0;
+        for (int pr = group; pr < p.n_pairs; pr += p.n_groups) {
+            for (int c = 0; c < p.chunks; ++c, ++it) {
+                const uint32_t stage = it % kStages, phase = (it / kStages) & 1;
+                mbar_wait(acc_empty, (it & 1) ^ 1);         // epilogue drained the accumulators
+                mbar_wait(b_full + stage, phase);           // spikes landed
+                tc_fence_after();
+                const uint64_t db_s = db0 + stage * b_stage;
+                if (elect_one()) {
+                    if (kKSteps > 0) {
+#pragma unroll
+                        for (int j = 0; j < kPlanes; ++j) {
+#pragma unroll
+                            for (int ks = 0; ks < kKSteps; ++ks)
+                                mma_i8(tmem_base + j * kN, da0 + (uint32_t)(j * kM * kKSteps * 2 + ks * a_kstep),
+                                       db_s + ks * b_kstep, idesc, ks > 0 ? 1u : 0u);
                         }
+                    } else {
+                        for (int j = 0; j < kPlanes; ++j)
+                            for (int ks = 0; ks < ksteps; ++ks)
+                                mma_i8(tmem_base + j * kN, da0 + j * a_plane + ks * a_kstep, db_s + ks * b_kstep,
+                                       idesc, ks > 0 ? 1u : 0u);
                     }
-                    tc_commit(b_empty + stage);    // smem slot reusable once these MMAs retire
-                    tc_commit(acc_full + buf);     // accumulators ready for the epilogue
                 }
+                __syncwarp();
+                if (elect_one()) {
+                    tc_commit(b_empty + stage);    // smem slot reusable once these MMAs retire
+                    tc_commit(acc_full);           // accumulators ready for the epilogue
+                }
+                __syncwarp();
             }
         }
     } else {
         // ===================== epilogue: IAF#2 scan, spike counts =====================
+        const int sp = (warp - 2) >> 2;                        // which stream of the pair
         const int quarter = warp & 3;                          // TMEM lanes this warp may touch
         const int row = quarter * 32 + lane;
         const int place = tile * kM + row;
-        const bool live = place < p.P;
-        const float scale = live ? p.scale[place] : 0.0f;
+        const bool live_place = place < p.P;
+        const float scale = live_place ? p.scale[place] : 0.0f;
         const float thr = p.thr, vmin = p.vmin;
         const int Q = p.steps / p.T;
+        const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + sp * kTileSteps;
         uint32_t it = 0;
-        for (int b = group; b < p.nb; b += p.n_groups) {
+        for (int pr = group; pr < p.n_pairs; pr += p.n_groups) {
+            const int b = 2 * pr + sp;
+            const bool live = live_place && b < p.nb;
             float v = live ? p.v2[(size_t)b * p.P + place] : 0.0f;
             float count = 0.0f;
             int t_in_q = 0, q = 0;
             for (int c = 0; c < p.chunks; ++c, ++it) {
-                const uint32_t buf = it % kAccBufs, aphase = (it / kAccBufs) & 1;
-                mbar_wait(acc_full + buf, aphase);
+                mbar_wait(acc_full, it & 1);
                 tc_fence_after();
-                const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * (kPlanes * kN);
-                const int nvalid = min(kN, p.steps - c * kN);
-#pragma unroll 1
-                for (int half = 0; half < kN / 16; ++half) {
-                    int32_t r[kPlanes][16];
+                // drain: three 16+16-bit partial sums per step, 96 registers
+                int32_t q0[kTileSteps], q1[kTileSteps], q2[kTileSteps];
 #pragma unroll
-                    for (int j = 0; j < kPlanes; ++j) tmem_ld16(tbase + j * kN + half * 16, r[j]);
-                    tmem_ld_wait();
+                for (int half = 0; half < 2; ++half) {
+                    int32_t lo[16], hi[16];
+                    tmem_ld16(tbase + 0 * kN + half * 16, lo); tmem_ld16(tbase + 1 * kN + half * 16, hi); tmem_ld_wait();
 #pragma unroll
-                    for (int n = 0; n < 16; ++n) {
-                        const int step_in_chunk = half * 16 + n;
-                        if (step_in_chunk < nvalid) {
-                            // X = sum_j P_j 256^j, exactly, in 64 bits
-                            const int32_t q0 = r[1][n] * 256 + r[0][n];
-                            const int32_t q1 = r[3][n] * 256 + r[2][n];
-                            const int32_t q2 = r[5][n] * 256 + r[4][n];
-                            const int64_t X = (int64_t)q0 + ((int64_t)q1 << 16) + ((int64_t)q2 << 32);
-                            const float x = __fmul_rn(__ll2float_rn(X), scale);
-                            const float s = iaf_out<kUnitThr>(v, x, thr, vmin);
-                            if (live) {
-                                if (p.out_steps)
-                                    p.out_steps[((size_t)b * p.steps + c * kN + step_in_chunk) * p.P + place] =
-                                        (uint8_t)fminf(s, 255.0f);
-                                count += s;
-                                if (++t_in_q == p.T) {
-                                    p.counts[((size_t)b * Q + q) * p.P + place] = count;
-                                    count = 0.0f; t_in_q = 0; ++q;
-                                }
+                    for (int n = 0; n < 16; ++n) q0[half * 16 + n] = hi[n] * 256 + lo[n];
+                    tmem_ld16(tbase + 2 * kN + half * 16, lo); tmem_ld16(tbase + 3 * kN + half * 16, hi); tmem_ld_wait();
+#pragma unroll
+                    for (int n = 0; n < 16; ++n) q1[half * 16 + n] = hi[n] * 256 + lo[n];
+                    tmem_ld16(tbase + 4 * kN + half * 16, lo); tmem_ld16(tbase + 5 * kN + half * 16, hi); tmem_ld_wait();
+#pragma unroll
+                    for (int n = 0; n < 16; ++n) q2[half * 16 + n] = hi[n] * 256 + lo[n];
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty);          // TMEM is free for the next tile's MMAs
+                if (!live) continue;
+                // x[n] = RN_f32(sum_j P_j 256^j) * 2^q for the whole tile first: 32 independent
+                // chains (int64 recombination, one cvt.rn.f32.s64, one exact power-of-two scale)
+                float x[kTileSteps];
+#pragma unroll
+                for (int n = 0; n < kTileSteps; ++n) {
+                    const int64_t X = (int64_t)q0[n] + ((int64_t)q1[n] << 16) + ((int64_t)q2[n] << 32);
+                    x[n] = __fmul_rn(__ll2float_rn(X), scale);
+                }
+                // then the serial IAF#2 scan over the tile's timesteps
+                const int nvalid = min(kTileSteps, p.steps - c * kTileSteps);
+                const int t_base = c * kTileSteps;
+                if (nvalid == kTileSteps && p.T - t_in_q > kTileSteps && !kDebug) {
+                    // common case: whole tile inside one query -> branch-free scan
+#pragma unroll
+                    for (int n = 0; n < kTileSteps; ++n) count += iaf_out<kUnitThr>(v, x[n], thr, vmin);
+                    t_in_q += kTileSteps;
+                } else {   // a query ends inside this tile, or ragged last tile of a stream
+#pragma unroll
+                    for (int n = 0; n < kTileSteps; ++n) {
+                        if (n < nvalid) {
+                            const float s = iaf_out<kUnitThr>(v, x[n], thr, vmin);
+                            if (kDebug) p.out_steps[((size_t)b * p.steps + t_base + n) * p.P + place] = (uint8_t)fminf(s, 255.0f);
+                            count += s;
+                            if (++t_in_q == p.T) {
+                                p.counts[((size_t)b * Q + q) * p.P + place] = count;
+                                count = 0.0f; t_in_q = 0; ++q;
                             }
                         }
                     }
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(acc_empty + buf);
             }
             if (live) p.v2[(size_t)b * p.P + place] = v;
         }
@@ -331,7 +400,7 @@ __global__ void __launch_bounds__(128) planes_kernel(const int64_t *__restrict__
 
 static size_t smem_bytes(int Fp)
 {
-    return (size_t)kPlanes * kM * Fp + (size_t)kStages * kN * Fp + (1 + 2 * kStages + 2 * kAccBufs) * 8 + 16;
+    return (size_t)kPlanes * kM * Fp + (size_t)kStages * kN * Fp + (3 + 2 * kStages) * 8 + 16;
 }
 
 }  // namespace tc
@@ -366,20 +435,32 @@ int snn_tc_output(SnnHandle *h, const int8_t *S1, int nb, int b0, int steps, flo
     p.planes = h->Wo_planes; p.S1 = S1; p.scale = h->Wo_scale;
     p.v2 = h->v2 + (size_t)b0 * h->P; p.counts = counts; p.out_steps = out_steps;
     p.P = h->P; p.Fp = h->Fp; p.T = h->T; p.steps = steps;
-    p.chunks = ceil_div(steps, kTileSteps); p.nb = nb;
+    p.chunks = ceil_div(steps, kTileSteps); p.nb = nb; p.n_pairs = (nb + 1) / 2;
     p.thr = h->thr; p.vmin = h->vmin;
     const int sms = std::max(sm_count(), 1);
-    p.n_groups = std::max(1, std::min(nb, sms / std::max(h->P_tiles, 1)));
+    p.n_groups = std::max(1, std::min(p.n_pairs, sms / std::max(h->P_tiles, 1)));
     const size_t smem = tc::smem_bytes(h->Fp);
     dim3 grid(h->P_tiles, p.n_groups);
     LaunchTimer timer(h, st, 1);
-    if (h->thr == 1.0f) {
-        LENS_CUDA(cudaFuncSetAttribute(tc::output_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc::output_tc_kernel<true><<<grid, tc::kThreads, smem, st>>>(p);
-    } else {
-        LENS_CUDA(cudaFuncSetAttribute(tc::output_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tc::output_tc_kernel<false><<<grid, tc::kThreads, smem, st>>>(p);
-    }
+    const bool unit = h->thr == 1.0f, dbg = out_steps != nullptr;
+#define LENS_TC_LAUNCH_K(U, D, K)                                                                                 \
+    do {                                                                                                          \
+        LENS_CUDA(cudaFuncSetAttribute(tc::output_tc_kernel<U, D, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                       (int)smem));                                                               \
+        tc::output_tc_kernel<U, D, K><<<grid, tc::kThreads, smem, st>>>(p);                                       \
+    } while (0)
+#define LENS_TC_LAUNCH(U, D)                                  \
+    do {                                                      \
+        if (h->Fp == 224) LENS_TC_LAUNCH_K(U, D, 7);          \
+        else if (h->Fp == 64) LENS_TC_LAUNCH_K(U, D, 2);      \
+        else LENS_TC_LAUNCH_K(U, D, 0);                       \
+    } while (0)
+    if (unit && !dbg) LENS_TC_LAUNCH(true, false);
+    else if (unit && dbg) LENS_TC_LAUNCH(true, true);
+    else if (!unit && !dbg) LENS_TC_LAUNCH(false, false);
+    else LENS_TC_LAUNCH(false, true);
+#undef LENS_TC_LAUNCH_K
+#undef LENS_TC_LAUNCH
     LENS_LAUNCH_CHECK();
     return 0;
 }
