@@ -256,7 +256,6 @@ __global__ void raster_thresholds_kernel(const float *__restrict__ U, int n, uin
 }
 
 constexpr int kRasterSlots = 4;      // streams processed concurrently by one CTA
-constexpr int kMaskWords = 8;        // I <= 256 inputs as a bitmask per timestep
 
 struct RasterParams {
     int I, F, Fp, T, Q, steps, nb;
@@ -276,14 +275,15 @@ struct RasterParams {
 // comparison above.  Persistent CTAs; each CTA keeps the whole fixed-point W_feat in shared
 // memory and runs kRasterSlots streams side by side (slot = blockDim.x / kRasterSlots threads,
 // thread f of a slot owns feature neuron f with its membrane potential in a register).
-// Per tile of 32 timesteps: (A) every warp builds input-spike bitmasks for some steps,
-// (C) every thread walks its 32 steps: exact int64 sum over the set bits, IAF#1, spike byte
-// into the slot's tile, (W) the tile leaves for HBM in the pair-tile layout.
-template <int kWords>
+// Per tile of 32 timesteps: (A) every warp compacts the active inputs of some steps into a list of
+// weight-row offsets, (C) every thread walks its 32 steps: exact int64 sum over the listed rows,
+// IAF#1, spike byte into the slot's tile, (W) the tile leaves for HBM in the pair-tile layout.
+template <bool kDebug>
 __global__ void __launch_bounds__(1024, 1) feature_raster_kernel(RasterParams p)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int I = p.I, F = p.F, Fp = p.Fp;
+    const int Ipad = (I + 31) & ~31;
     const int slot_threads = blockDim.x / kRasterSlots;
     const int slot = threadIdx.x / slot_threads;
     const int f = threadIdx.x - slot * slot_threads;
@@ -292,8 +292,10 @@ __global__ void __launch_bounds__(1024, 1) feature_raster_kernel(RasterParams p)
     int64_t *sW = reinterpret_cast<int64_t *>(smem_raw);                       // [I][F]
     uint8_t *sUq = reinterpret_cast<uint8_t *>(sW + (size_t)I * F);            // [T][I]
     size_t off = ((size_t)I * F * 8 + (size_t)p.T * I + 15) & ~(size_t)15;
-    uint32_t *sMask = reinterpret_cast<uint32_t *>(smem_raw + off) + slot * (kChunk * kWords);   // [kChunk][kWords]
-    off += (size_t)kRasterSlots * kChunk * kWords * 4;
+    uint8_t *sList = smem_raw + off + (size_t)slot * kChunk * Ipad;           // [kChunk][Ipad] active input indices
+    off += (size_t)kRasterSlots * kChunk * Ipad;
+    int *sCnt = reinterpret_cast<int *>(smem_raw + off) + slot * kChunk;       // [kChunk] active inputs per step
+    off += (size_t)kRasterSlots * kChunk * 4;
     uint8_t *tile = smem_raw + off + (size_t)slot * kChunk * Fp;               // [Fp/16][kChunk][16]
 
     for (int i = threadIdx.x; i < I * F; i += blockDim.x) sW[i] = p.Wf_fx[i];
@@ -301,6 +303,7 @@ __global__ void __launch_bounds__(1024, 1) feature_raster_kernel(RasterParams p)
     const float scale = (f < F) ? p.Wf_scale[f] : 0.0f;
     const float vmin = p.vmin;
     const int n_chunks = (p.steps + kChunk - 1) / kChunk;
+    const int64_t *wcol = sW + (f < F ? f : 0);
     int64_t n_over = 0;
     __syncthreads();
 
@@ -312,45 +315,48 @@ __global__ void __launch_bounds__(1024, 1) feature_raster_kernel(RasterParams p)
         for (int ch = 0; ch < n_chunks; ++ch) {
             const int t0 = ch * kChunk;
             const int nc = min(kChunk, p.steps - t0);
-            // ---- (A) input-spike bitmasks of this tile's steps
+            // ---- (A) active-input lists of this tile's steps
             if (live) {
                 for (int c = slot_warp; c < nc; c += slot_warps) {
                     const int step = t0 + c;
                     const int q = step / p.T, t = step - q * p.T;
                     const uint8_t *px = p.pooled + ((size_t)b * p.Q + q) * I;
                     const uint8_t *uq = sUq + (size_t)t * I;
-#pragma unroll
-                    for (int w = 0; w < kWords; ++w) {
-                        const int i = w * 32 + lane;
+                    uint8_t *lst = sList + c * Ipad;
+                    int base = 0;
+                    for (int i0 = 0; i0 < I; i0 += 32) {
+                        const int i = i0 + lane;
                         const bool spike = (i < I) && (__ldg(px + i) > uq[i]);
                         const unsigned m = __ballot_sync(0xffffffffu, spike);
-                        if (lane == 0) sMask[c * kWords + w] = m;
+                        if (spike) lst[base + __popc(m & ((1u << lane) - 1))] = (uint8_t)i;
+                        base += __popc(m);
                     }
+                    if (lane == 0) sCnt[c] = base;
                 }
             }
             __syncthreads();
-            // ---- (C) exact contraction over the set bits + IAF#1
+            // ---- (C) exact contraction over the listed weight rows + IAF#1
             if (live && f < F) {
                 for (int c = 0; c < nc; ++c) {
+                    const int n = sCnt[c];
+                    const uint8_t *lst = sList + c * Ipad;
                     int64_t acc = 0;
-#pragma unroll
-                    for (int w = 0; w < kWords; ++w) {
-                        unsigned m = sMask[c * kWords + w];
-                        while (m) {
-                            const int i = w * 32 + __ffs(m) - 1;
-                            m &= m - 1;
-                            acc += sW[i * F + f];
-                        }
-                    }
+#pragma unroll 1
+                    for (int a = 0; a < n; ++a) acc += wcol[(int)lst[a] * F];
                     const float x = __fmul_rn(__ll2float_rn(acc), scale);
                     float vv = __fadd_rn(v1, x);                // IAF#1 with thr == 1 (see iaf_step)
                     float s = (vv >= 1.0f) ? 1.0f : 0.0f;
-                    if (vv >= 2.0f) s = truncf(vv);
-                    vv = __fsub_rn(vv, s);
+                    uint32_t sb = (vv >= 1.0f) ? 1u : 0u;
+                    if (vv >= 2.0f) {                           // rare: several spikes in one step
+                        s = truncf(vv);
+                        float sc = s;
+                        if (sc > (float)LENS_MAX_SPIKE) { sc = (float)LENS_MAX_SPIKE; ++n_over; }
+                        sb = (uint32_t)sc;
+                    }
+                    vv = __fsub_rn(vv, s);                      // exact: s is the integer part of vv
                     v1 = __fadd_rn(fmaxf(__fsub_rn(vv, vmin), 0.0f), vmin);
-                    if (s > (float)LENS_MAX_SPIKE) { s = (float)LENS_MAX_SPIKE; ++n_over; }
-                    tile[s1_byte_in_half(c, f)] = (uint8_t)s;
-                    if (p.hidden_steps) p.hidden_steps[((size_t)b * p.steps + t0 + c) * F + f] = (uint8_t)s;
+                    tile[s1_byte_in_half(c, f)] = (uint8_t)sb;
+                    if (kDebug) p.hidden_steps[((size_t)b * p.steps + t0 + c) * F + f] = (uint8_t)sb;
                 }
                 for (int c = nc; c < kChunk; ++c) tile[s1_byte_in_half(c, f)] = 0;   // ragged last tile
             } else if (live && f < Fp) {
@@ -372,18 +378,18 @@ __global__ void __launch_bounds__(1024, 1) feature_raster_kernel(RasterParams p)
     if (n_over) atomicAdd((unsigned long long *)p.overflow, (unsigned long long)n_over);
 }
 
-static size_t raster_smem_bytes(const SnnHandle *h, int words)
+static size_t raster_smem_bytes(const SnnHandle *h)
 {
+    const int Ipad = (h->I + 31) & ~31;
     size_t off = ((size_t)h->I * h->F * 8 + (size_t)h->T * h->I + 15) & ~(size_t)15;
-    return off + (size_t)kRasterSlots * kChunk * words * 4 + (size_t)kRasterSlots * kChunk * h->Fp;
+    return off + (size_t)kRasterSlots * kChunk * Ipad + (size_t)kRasterSlots * kChunk * 4 +
+           (size_t)kRasterSlots * kChunk * h->Fp;
 }
-
-static int raster_words(const SnnHandle *h) { return h->I <= 128 ? 4 : 8; }
 
 static bool raster_path_ok(const SnnHandle *h)
 {
-    return h->Uq && h->thr == 1.0f && !h->v0_dirty && h->I <= 32 * kMaskWords &&
-           h->Fp * kRasterSlots <= 1024 && raster_smem_bytes(h, raster_words(h)) <= 227 * 1024;
+    return h->Uq && h->thr == 1.0f && !h->v0_dirty && h->I <= 256 &&
+           h->Fp * kRasterSlots <= 1024 && raster_smem_bytes(h) <= 227 * 1024;
 }
 
 static int launch_feature_raster(SnnHandle *h, const uint8_t *pooled, int b0, int nb, int steps,
@@ -393,17 +399,16 @@ static int launch_feature_raster(SnnHandle *h, const uint8_t *pooled, int b0, in
     p.I = h->I; p.F = h->F; p.Fp = h->Fp; p.T = h->T; p.Q = steps / h->T; p.steps = steps; p.nb = nb;
     p.vmin = h->vmin; p.Wf_fx = h->Wf_fx; p.Wf_scale = h->Wf_scale; p.Uq = h->Uq; p.pooled = pooled;
     p.v1 = h->v1 + (size_t)b0 * h->F; p.S1 = h->S1; p.hidden_steps = hidden_steps; p.overflow = h->counters;
-    const int words = raster_words(h);
-    const size_t smem = raster_smem_bytes(h, words);
+    const size_t smem = raster_smem_bytes(h);
     const int threads = kRasterSlots * h->Fp;
     const int grid = std::min(std::max(sm_count(), 1), ceil_div(nb, kRasterSlots));
     LaunchTimer timer(h, st, 0);
-    if (words == 4) {
-        LENS_CUDA(cudaFuncSetAttribute(feature_raster_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        feature_raster_kernel<4><<<grid, threads, smem, st>>>(p);
+    if (hidden_steps) {
+        LENS_CUDA(cudaFuncSetAttribute(feature_raster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        feature_raster_kernel<true><<<grid, threads, smem, st>>>(p);
     } else {
-        LENS_CUDA(cudaFuncSetAttribute(feature_raster_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        feature_raster_kernel<8><<<grid, threads, smem, st>>>(p);
+        LENS_CUDA(cudaFuncSetAttribute(feature_raster_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        feature_raster_kernel<false><<<grid, threads, smem, st>>>(p);
     }
     LENS_LAUNCH_CHECK();
     return 0;

@@ -168,17 +168,19 @@ struct Params {
 };
 
 // One IAF#2 step on the exact contraction result.
-template <bool kUnitThr>
+// kUnit: thr == 1 and v_min == -1 (the reference's fixed configuration, lens/run_model.py:151-156).
+// Then v / thr == v and s * thr == s exactly, (v > 0) * trunc(v / thr) is 0 below 1, 1 in [1, 2) and
+// trunc(v) above, and t = v - s is exact (s is the integer part of v), so the clip
+// relu(t - v_min) + v_min == relu(fl(v + (1 - s))) - 1 rounds exactly like the reference's three ops.
+template <bool kUnit>
 __device__ __forceinline__ float iaf_out(float &v, float x, float thr, float vmin)
 {
-    if (kUnitThr) {
-        // thr == 1: v / thr == v and s * thr == s exactly, so (v > 0) * trunc(v / thr) is
-        // 0 below 1, 1 in [1, 2) and trunc(v) above (rare: more than one spike in a step)
-        float vv = __fadd_rn(v, x);
+    if (kUnit) {
+        const float vv = __fadd_rn(v, x);
         float s = (vv >= 1.0f) ? 1.0f : 0.0f;
-        if (vv >= 2.0f) s = truncf(vv);
-        vv = __fsub_rn(vv, s);
-        v = __fadd_rn(fmaxf(__fsub_rn(vv, vmin), 0.0f), vmin);
+        float c = (vv >= 1.0f) ? 0.0f : 1.0f;          // 1 - s
+        if (vv >= 2.0f) { s = truncf(vv); c = 1.0f - s; }   // rare: several spikes in one step
+        v = __fadd_rn(fmaxf(__fadd_rn(vv, c), 0.0f), -1.0f);
         return s;
     }
     return iaf_step(v, x, thr, vmin);
@@ -442,7 +444,7 @@ int snn_tc_output(SnnHandle *h, const int8_t *S1, int nb, int b0, int steps, flo
     const size_t smem = tc::smem_bytes(h->Fp);
     dim3 grid(h->P_tiles, p.n_groups);
     LaunchTimer timer(h, st, 1);
-    const bool unit = h->thr == 1.0f, dbg = out_steps != nullptr;
+    const bool unit = h->thr == 1.0f && h->vmin == -1.0f, dbg = out_steps != nullptr;
 #define LENS_TC_LAUNCH_K(U, D, K)                                                                                 \
     do {                                                                                                          \
         LENS_CUDA(cudaFuncSetAttribute(tc::output_tc_kernel<U, D, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, \

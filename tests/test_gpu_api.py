@@ -1,0 +1,125 @@
+"""GPU tests of the reference-facing Python API (LENS, run_inference, recallAtK) on the bundled
+example data (committed as fixtures by tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def write_png_u8(path, frame):
+    from torchvision.io import write_png
+    write_png(torch.from_numpy(frame)[None].contiguous(), path)
+
+
+@pytest.fixture()
+def example_tree(tmp_path, golden):
+    """Recreate the reference's on-disk layout (dataset PNGs + CSV + GT + .pth) from a golden npz."""
+    def make(name, dataset, camera, reference, query):
+        g = golden(name)
+        root = tmp_path / "lens"
+        qdir = root / "dataset" / dataset / camera / query
+        rdir = root / "dataset" / dataset / camera / reference
+        os.makedirs(qdir), os.makedirs(rdir), os.makedirs(root / "models"), os.makedirs(root / "output")
+        names = []
+        for i, fr in enumerate(g["frames"]):
+            n = f"image_{i:04d}.png"
+            write_png_u8(str(qdir / n), fr)
+            names.append(n)
+        with open(root / "dataset" / (query + ".csv"), "w") as f:
+            f.write("Image_name,index\n" + "".join(f"{n},{i}\n" for i, n in enumerate(names)))
+        np.save(root / "dataset" / dataset / camera / f"{reference}_{query}_GT.npy", g["GT"])
+        F, I = g["W_feat"].shape
+        P = g["W_out"].shape[0]
+        sd = {"feature_layer.thr": torch.zeros(1, F), "feature_layer.w.weight": torch.from_numpy(g["W_feat"]),
+              "output_layer.thr": torch.zeros(1, P), "output_layer.w.weight": torch.from_numpy(g["W_out"])}
+        torch.save(sd, root / "models" / f"{reference}_LENS_IN{I}_FN{F}_DB{P}.pth")
+        return g, root
+    return make
+
+
+def test_run_inference_example(example_tree, monkeypatch):
+    """python main.py --sim_mat --matching on the bundled example: same similarity matrix, same
+    sequence-matched matrix, Recall@N equal to the reference's formula under the stable tie rule and
+    inside the tie bounds of the reference's own (unstable-argsort) numbers."""
+    from lens_b200.config import default_args, generate_model_name
+    from lens_b200.run_model import LENS, run_inference
+    g, root = example_tree("config1", "example", "davis128", "example-reference", "example-query")
+    monkeypatch.chdir(root.parent)
+    args = default_args(matching=True, sim_mat=True, data_dir=str(root / "dataset") + "/")
+    args.quiet = True
+    model = LENS(args)
+    name = generate_model_name(model)
+    assert name == "example-reference_LENS_IN100_FN200_DB100.pth"
+    R = run_inference(model, name, models_dir=str(root / "models"))
+    assert np.array_equal(model.similarity.cpu().numpy(), g["S"].astype(np.float32))
+    assert np.array_equal(model.dist_matrix_seq, g["D"])
+    assert np.array_equal(model.GTtol, g["GTtol"])
+    want = [round(O.recall_at_k(g["D"], g["GTtol"], K=n, kind="stable"), 2) for n in (1, 5, 10, 15, 20, 25)]
+    assert R == want
+    for r, ref, n in zip(R, g["R"], (1, 5, 10, 15, 20, 25)):
+        lo, hi = O.recall_bounds(g["D"], g["GTtol"], n)
+        assert round(lo, 2) - 1e-9 <= r <= round(hi, 2) + 1e-9
+        assert round(lo, 2) - 1e-9 <= ref <= round(hi, 2) + 1e-9
+    assert os.path.exists(os.path.join(model.output_folder, "lens.log"))
+
+
+def test_seam_loop_equals_fast_path(example_tree, monkeypatch):
+    """The reference's per-query loop through `sinabs_model(spikes)` (run_model.py:234-241) and the
+    batched run_streams fast path give the same similarity rows."""
+    from lens_b200.config import default_args, generate_model_name
+    from lens_b200.run_model import LENS
+    from lens_b200.src.dataset import CustomImageDataset, ProcessImage
+    g, root = example_tree("config1", "example", "davis128", "example-reference", "example-query")
+    monkeypatch.chdir(root.parent)
+    args = default_args(matching=False, data_dir=str(root / "dataset") + "/", query_places=6)
+    args.quiet = True
+    model = LENS(args)
+    model.load_model(str(root / "models" / generate_model_name(model)))
+    ds = CustomImageDataset(model.dataset_file, model.query_dir, model.kernel_size, transform=ProcessImage(),
+                            skip=1, max_samples=6, is_spiking=True, time_window=model.timebin)
+    model.build_network()
+    rows = []
+    for i in range(len(ds)):
+        spikes, label, _, _ = ds[i]                       # [T, 1, roi, roi] float raster (reference format)
+        assert label == i
+        out = model.sinabs_model(spikes.cuda())            # [T, P]
+        rows.append(out.sum(dim=0))
+    S_loop = torch.stack(rows).cpu().numpy()
+    assert np.array_equal(S_loop, g["S"][:6].astype(np.float32))
+    model.build_network()                                  # fresh state
+    S_fast = model.similarity_matrix(ds).cpu().numpy()
+    assert np.array_equal(S_fast, S_loop)
+
+
+def test_recallAtK_signature(golden):
+    from lens_b200.src.metrics import recallAtK
+    g = golden("config1")
+    D, GT = g["D"], g["GTtol"]
+    for K in (1, 5, 25):
+        assert abs(recallAtK(D, GT, K=K) - O.recall_at_k(D, GT, K=K, kind="stable")) < 1e-12
+    soft = np.roll(GT, 1, axis=0) | GT
+    assert abs(recallAtK(D, GT, GTsoft=soft, K=5) - O.recall_at_k(D, GT, GTsoft=soft, K=5, kind="stable")) < 1e-12
+    with pytest.raises(AssertionError):
+        recallAtK(D, GT[:-1], K=1)
+
+
+def test_sequence_length_zero_branch(example_tree, monkeypatch):
+    """sequence_length = 0 keeps the raw similarity matrix (run_model.py:254)."""
+    from lens_b200.config import default_args, generate_model_name
+    from lens_b200.run_model import LENS, run_inference
+    g, root = example_tree("config1", "example", "davis128", "example-reference", "example-query")
+    monkeypatch.chdir(root.parent)
+    args = default_args(matching=True, sequence_length=0, data_dir=str(root / "dataset") + "/")
+    args.quiet = True
+    model = LENS(args)
+    R = run_inference(model, generate_model_name(model), models_dir=str(root / "models"))
+    S = g["S"].astype(np.float64)
+    assert np.array_equal(model.dist_matrix_seq, S)
+    GTtol = O.make_gt_tol(g["GT"], 0, 3)
+    want = [round(O.recall_at_k(S, GTtol, K=n, kind="stable"), 2) for n in (1, 5, 10, 15, 20, 25)]
+    assert R == want
