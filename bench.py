@@ -234,14 +234,14 @@ def main():
         torch.cuda.synchronize()
         return [a.elapsed_time(b) for a, b in evs]
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                      # samples through warm-up and both timed regions
     for _ in range(max(args.warmup, 3)):
         step_resident()
     for _ in range(2):
         step_e2e()
-    sampler = ClockSampler(local)
     barrier()
-    if rank == 0:
-        sampler.start()
     pipe.net.set_timing(True)
     launches0 = _lib.launch_count()
     barrier()

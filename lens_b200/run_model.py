@@ -138,9 +138,7 @@ class LENS(nn.Module):
         self.GTtol = GTtol
 
         if getattr(self, "PR_curve", False):
-            from .src.pr import createPR
-            P_, R_ = createPR(dist_matrix_seq.T, GTtol.T, self.output_folder, matching="single", n_thresh=100)
-            self.lens_PR = {"Precision": P_, "Recall": R_}
+            raise LensError("--PR_curve (createPR, SURVEY 8f-1) is not part of lens_b200 yet")
         if getattr(self, "sad", False):
             raise LensError("--sad (sum-of-absolute-differences baseline) is not part of lens_b200 yet")
 
