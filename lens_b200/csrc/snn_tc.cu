@@ -202,9 +202,9 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
     uint64_t *a_full = bars;                                 // [1]
     uint64_t *b_full = bars + 1;                             // [kStages]
     uint64_t *b_empty = b_full + kStages;                    // [kStages]
-    uint64_t *acc_full = b_empty + kStages;                  // [1]
-    uint64_t *acc_empty = acc_full + 1;                      // [1]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 1);
+    uint64_t *acc_full = b_empty + kStages;                  // [3] one per plane pair
+    uint64_t *acc_empty = acc_full + 3;                      // [3]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 3);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x;          // place tile
@@ -213,8 +213,10 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
     if (threadIdx.x == 0) {
         mbar_init(a_full, 1);
         for (int i = 0; i < kStages; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
-        mbar_init(acc_full, 1);
-        mbar_init(acc_empty, 8);          // one arrival per epilogue warp
+        for (int i = 0; i < 3; ++i) {
+            mbar_init(acc_full + i, 1);
+            mbar_init(acc_empty + i, 8);  // one arrival per epilogue warp
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {   // TMEM allocation (whole warp), address lands in shared memory
@@ -263,30 +265,34 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
         for (int pr = group; pr < p.n_pairs; pr += p.n_groups) {
             for (int c = 0; c < p.chunks; ++c, ++it) {
                 const uint32_t stage = it % kStages, phase = (it / kStages) & 1;
-                mbar_wait(acc_empty, (it & 1) ^ 1);         // epilogue drained the accumulators
                 mbar_wait(b_full + stage, phase);           // spikes landed
-                tc_fence_after();
                 const uint64_t db_s = db0 + stage * b_stage;
-                if (elect_one()) {
-                    if (kKSteps > 0) {
+                // The accumulator set is handed over in plane pairs: the MMAs of pair g of this tile
+                // start as soon as the epilogue has drained pair g of the previous tile, and the
+                // epilogue starts draining pair g while pairs g+1.. are still being computed.
 #pragma unroll
-                        for (int j = 0; j < kPlanes; ++j) {
+                for (int g = 0; g < 3; ++g) {
+                    mbar_wait(acc_empty + g, (it & 1) ^ 1);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        if (kKSteps > 0) {
 #pragma unroll
-                            for (int ks = 0; ks < kKSteps; ++ks)
-                                mma_i8(tmem_base + j * kN, da0 + (uint32_t)(j * kM * kKSteps * 2 + ks * a_kstep),
-                                       db_s + ks * b_kstep, idesc, ks > 0 ? 1u : 0u);
+                            for (int j = 2 * g; j < 2 * g + 2; ++j) {
+#pragma unroll
+                                for (int ks = 0; ks < kKSteps; ++ks)
+                                    mma_i8(tmem_base + j * kN, da0 + (uint32_t)(j * kM * kKSteps * 2 + ks * a_kstep),
+                                           db_s + ks * b_kstep, idesc, ks > 0 ? 1u : 0u);
+                            }
+                        } else {
+                            for (int j = 2 * g; j < 2 * g + 2; ++j)
+                                for (int ks = 0; ks < ksteps; ++ks)
+                                    mma_i8(tmem_base + j * kN, da0 + j * a_plane + ks * a_kstep, db_s + ks * b_kstep,
+                                           idesc, ks > 0 ? 1u : 0u);
                         }
-                    } else {
-                        for (int j = 0; j < kPlanes; ++j)
-                            for (int ks = 0; ks < ksteps; ++ks)
-                                mma_i8(tmem_base + j * kN, da0 + j * a_plane + ks * a_kstep, db_s + ks * b_kstep,
-                                       idesc, ks > 0 ? 1u : 0u);
+                        tc_commit(acc_full + g);               // this pair is ready for the epilogue
+                        if (g == 2) tc_commit(b_empty + stage); // smem slot reusable once all MMAs retire
                     }
-                }
-                __syncwarp();
-                if (elect_one()) {
-                    tc_commit(b_empty + stage);    // smem slot reusable once these MMAs retire
-                    tc_commit(acc_full);           // accumulators ready for the epilogue
+                    __syncwarp();
                 }
                 __syncwarp();
             }
@@ -310,26 +316,31 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
             float count = 0.0f;
             int t_in_q = 0, q = 0;
             for (int c = 0; c < p.chunks; ++c, ++it) {
-                mbar_wait(acc_full, it & 1);
-                tc_fence_after();
-                // drain: three 16+16-bit partial sums per step, 96 registers
+                // drain: three 16+16-bit partial sums per step, 96 registers; each plane pair is
+                // returned to the MMA warp as soon as it has been read
                 int32_t q0[kTileSteps], q1[kTileSteps], q2[kTileSteps];
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    int32_t lo[16], hi[16];
-                    tmem_ld16(tbase + 0 * kN + half * 16, lo); tmem_ld16(tbase + 1 * kN + half * 16, hi); tmem_ld_wait();
+                for (int g = 0; g < 3; ++g) {
+                    mbar_wait(acc_full + g, it & 1);
+                    tc_fence_after();
 #pragma unroll
-                    for (int n = 0; n < 16; ++n) q0[half * 16 + n] = hi[n] * 256 + lo[n];
-                    tmem_ld16(tbase + 2 * kN + half * 16, lo); tmem_ld16(tbase + 3 * kN + half * 16, hi); tmem_ld_wait();
+                    for (int half = 0; half < 2; ++half) {
+                        int32_t lo[16], hi[16];
+                        tmem_ld16(tbase + (2 * g) * kN + half * 16, lo);
+                        tmem_ld16(tbase + (2 * g + 1) * kN + half * 16, hi);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int n = 0; n < 16; ++n) q1[half * 16 + n] = hi[n] * 256 + lo[n];
-                    tmem_ld16(tbase + 4 * kN + half * 16, lo); tmem_ld16(tbase + 5 * kN + half * 16, hi); tmem_ld_wait();
-#pragma unroll
-                    for (int n = 0; n < 16; ++n) q2[half * 16 + n] = hi[n] * 256 + lo[n];
+                        for (int n = 0; n < 16; ++n) {
+                            const int32_t qq = hi[n] * 256 + lo[n];
+                            if (g == 0) q0[half * 16 + n] = qq;
+                            else if (g == 1) q1[half * 16 + n] = qq;
+                            else q2[half * 16 + n] = qq;
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty + g);   // pair g is free for the next tile's MMAs
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(acc_empty);          // TMEM is free for the next tile's MMAs
                 if (!live) continue;
                 // x[n] = RN_f32(sum_j P_j 256^j) * 2^q for the whole tile first: 32 independent
                 // chains (int64 recombination, one cvt.rn.f32.s64, one exact power-of-two scale)
@@ -342,12 +353,42 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
                 // then the serial IAF#2 scan over the tile's timesteps
                 const int nvalid = min(kTileSteps, p.steps - c * kTileSteps);
                 const int t_base = c * kTileSteps;
-                if (nvalid == kTileSteps && p.T - t_in_q > kTileSteps && !kDebug) {
-                    // common case: whole tile inside one query -> branch-free scan
+                bool redo = true;
+                if (kUnitThr && !kDebug && nvalid == kTileSteps && p.T >= kTileSteps) {
+                    // Fast path: at most one spike per step is assumed (checked; a tile that turns out
+                    // to hold a multi-spike step is redone below), which keeps the loop-carried chain at
+                    // FADD -> FSET -> FADD -> FMNMX -> FADD.  A query may end inside the tile: the spikes of
+                    // steps <= nb go to the ending query, the rest to the next one.
+                    const int nb = p.T - 1 - t_in_q;                 // tile-local index of the query's last step
+                    const float v_start = v;
+                    float cnt_all = 0.0f, cnt_head = 0.0f;
+                    bool multi = false;
 #pragma unroll
-                    for (int n = 0; n < kTileSteps; ++n) count += iaf_out<kUnitThr>(v, x[n], thr, vmin);
-                    t_in_q += kTileSteps;
-                } else {   // a query ends inside this tile, or ragged last tile of a stream
+                    for (int n = 0; n < kTileSteps; ++n) {
+                        const float vv = __fadd_rn(v, x[n]);
+                        const float s = (vv >= 1.0f) ? 1.0f : 0.0f;
+                        const float cc = (vv >= 1.0f) ? 0.0f : 1.0f;  // 1 - s
+                        multi |= (vv >= 2.0f);
+                        v = __fadd_rn(fmaxf(__fadd_rn(vv, cc), 0.0f), -1.0f);
+                        cnt_all += s;
+                        if (n <= nb) cnt_head += s;
+                    }
+                    if (!multi) {
+                        redo = false;
+                        if (nb < kTileSteps) {                        // the query ends in this tile
+                            p.counts[((size_t)b * Q + q) * p.P + place] = count + cnt_head;
+                            count = cnt_all - cnt_head;
+                            t_in_q = kTileSteps - 1 - nb;
+                            ++q;
+                        } else {
+                            count += cnt_all;
+                            t_in_q += kTileSteps;
+                        }
+                    } else {
+                        v = v_start;
+                    }
+                }
+                if (redo) {   // generic: multi-spike steps, ragged last tile, debug output, tiny T
 #pragma unroll
                     for (int n = 0; n < kTileSteps; ++n) {
                         if (n < nvalid) {
@@ -402,7 +443,7 @@ __global__ void __launch_bounds__(128) planes_kernel(const int64_t *__restrict__
 
 static size_t smem_bytes(int Fp)
 {
-    return (size_t)kPlanes * kM * Fp + (size_t)kStages * kN * Fp + (3 + 2 * kStages) * 8 + 16;
+    return (size_t)kPlanes * kM * Fp + (size_t)kStages * kN * Fp + (7 + 2 * kStages) * 8 + 16;
 }
 
 }  // namespace tc
