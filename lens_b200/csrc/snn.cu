@@ -278,6 +278,42 @@ struct RasterParams {
 // Per tile of 32 timesteps: (A) every warp compacts the active inputs of some steps into a list of
 // weight-row offsets, (C) every thread walks its 32 steps: exact int64 sum over the listed rows,
 // IAF#1, spike byte into the slot's tile, (W) the tile leaves for HBM in the pair-tile layout.
+// shared-memory accessors on 32-bit shared-window addresses (keeps the hot loop free of
+// generic-to-shared address conversions)
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a)
+{
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ int64_t lds_s64(uint32_t a)
+{
+    int64_t v;
+    asm volatile("ld.shared.s64 %0, [%1];" : "=l"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ int lds_s32(uint32_t a)
+{
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v)
+{
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+
+// slow path of IAF#1: more than one spike in a step (kept out of line so the hot loop stays short);
+// returns trunc(vv) and, in the low byte of `packed`, the spike count clipped to LENS_MAX_SPIKE
+// (bit 8 set when it had to be clipped)
+__device__ __noinline__ float multi_spike(float vv, uint32_t *packed)
+{
+    const float s = truncf(vv);
+    const bool over = s > (float)LENS_MAX_SPIKE;
+    *packed = (uint32_t)(over ? (float)LENS_MAX_SPIKE : s) | (over ? 256u : 0u);
+    return s;
+}
+
 template <bool kDebug>
 __global__ void __launch_bounds__(1024, 1) feature_raster_kernel(RasterParams p)
 {
@@ -290,20 +326,21 @@ __global__ void __launch_bounds__(1024, 1) feature_raster_kernel(RasterParams p)
     const int lane = threadIdx.x & 31;
     const int slot_warp = f >> 5, slot_warps = slot_threads >> 5;
     int64_t *sW = reinterpret_cast<int64_t *>(smem_raw);                       // [I][F]
-    uint8_t *sUq = reinterpret_cast<uint8_t *>(sW + (size_t)I * F);            // [T][I]
-    size_t off = ((size_t)I * F * 8 + (size_t)p.T * I + 15) & ~(size_t)15;
-    uint8_t *sList = smem_raw + off + (size_t)slot * kChunk * Ipad;           // [kChunk][Ipad] active input indices
-    off += (size_t)kRasterSlots * kChunk * Ipad;
+    size_t off = ((size_t)I * F * 8 + 15) & ~(size_t)15;
+    uint16_t *sList = reinterpret_cast<uint16_t *>(smem_raw + off) + (size_t)slot * kChunk * Ipad;  // [kChunk][Ipad] i*F
+    off += (size_t)kRasterSlots * kChunk * Ipad * 2;
     int *sCnt = reinterpret_cast<int *>(smem_raw + off) + slot * kChunk;       // [kChunk] active inputs per step
     off += (size_t)kRasterSlots * kChunk * 4;
     uint8_t *tile = smem_raw + off + (size_t)slot * kChunk * Fp;               // [Fp/16][kChunk][16]
 
     for (int i = threadIdx.x; i < I * F; i += blockDim.x) sW[i] = p.Wf_fx[i];
-    for (int i = threadIdx.x; i < p.T * I; i += blockDim.x) sUq[i] = p.Uq[i];
     const float scale = (f < F) ? p.Wf_scale[f] : 0.0f;
     const float vmin = p.vmin;
     const int n_chunks = (p.steps + kChunk - 1) / kChunk;
-    const int64_t *wcol = sW + (f < F ? f : 0);
+    const uint32_t a_w = (uint32_t)__cvta_generic_to_shared(sW) + 8u * (uint32_t)(f < F ? f : 0);
+    const uint32_t a_list = (uint32_t)__cvta_generic_to_shared(sList);
+    const uint32_t a_cnt = (uint32_t)__cvta_generic_to_shared(sCnt);
+    const uint32_t a_tile = (uint32_t)__cvta_generic_to_shared(tile) + (uint32_t)((f >> 4) * (kChunk * 16) + (f & 15));
     int64_t n_over = 0;
     __syncthreads();
 
@@ -315,20 +352,20 @@ __global__ void __launch_bounds__(1024, 1) feature_raster_kernel(RasterParams p)
         for (int ch = 0; ch < n_chunks; ++ch) {
             const int t0 = ch * kChunk;
             const int nc = min(kChunk, p.steps - t0);
-            // ---- (A) active-input lists of this tile's steps
+            // ---- (A) active-input lists of this tile's steps (entries = weight-row offsets i * F)
             if (live) {
                 for (int c = slot_warp; c < nc; c += slot_warps) {
                     const int step = t0 + c;
                     const int q = step / p.T, t = step - q * p.T;
                     const uint8_t *px = p.pooled + ((size_t)b * p.Q + q) * I;
-                    const uint8_t *uq = sUq + (size_t)t * I;
-                    uint8_t *lst = sList + c * Ipad;
+                    const uint8_t *uq = p.Uq + (size_t)t * I;
+                    uint16_t *lst = sList + c * Ipad;
                     int base = 0;
                     for (int i0 = 0; i0 < I; i0 += 32) {
                         const int i = i0 + lane;
-                        const bool spike = (i < I) && (__ldg(px + i) > uq[i]);
+                        const bool spike = (i < I) && (__ldg(px + i) > __ldg(uq + i));
                         const unsigned m = __ballot_sync(0xffffffffu, spike);
-                        if (spike) lst[base + __popc(m & ((1u << lane) - 1))] = (uint8_t)i;
+                        if (spike) lst[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)(i * F);
                         base += __popc(m);
                     }
                     if (lane == 0) sCnt[c] = base;
@@ -337,25 +374,26 @@ __global__ void __launch_bounds__(1024, 1) feature_raster_kernel(RasterParams p)
             __syncthreads();
             // ---- (C) exact contraction over the listed weight rows + IAF#1
             if (live && f < F) {
-                for (int c = 0; c < nc; ++c) {
-                    const int n = sCnt[c];
-                    const uint8_t *lst = sList + c * Ipad;
+                uint32_t al = a_list, ac = a_cnt, at = a_tile;
+#pragma unroll 1
+                for (int c = 0; c < nc; ++c, al += 2 * Ipad, ac += 4, at += 16) {
+                    const int n = lds_s32(ac);
                     int64_t acc = 0;
 #pragma unroll 1
-                    for (int a = 0; a < n; ++a) acc += wcol[(int)lst[a] * F];
+                    for (uint32_t a = al, ae = al + 2 * n; a != ae; a += 2) acc += lds_s64(a_w + 8u * lds_u16(a));
                     const float x = __fmul_rn(__ll2float_rn(acc), scale);
                     float vv = __fadd_rn(v1, x);                // IAF#1 with thr == 1 (see iaf_step)
                     float s = (vv >= 1.0f) ? 1.0f : 0.0f;
                     uint32_t sb = (vv >= 1.0f) ? 1u : 0u;
                     if (vv >= 2.0f) {                           // rare: several spikes in one step
-                        s = truncf(vv);
-                        float sc = s;
-                        if (sc > (float)LENS_MAX_SPIKE) { sc = (float)LENS_MAX_SPIKE; ++n_over; }
-                        sb = (uint32_t)sc;
+                        uint32_t packed;
+                        s = multi_spike(vv, &packed);
+                        sb = packed & 255u;
+                        n_over += packed >> 8;
                     }
                     vv = __fsub_rn(vv, s);                      // exact: s is the integer part of vv
                     v1 = __fadd_rn(fmaxf(__fsub_rn(vv, vmin), 0.0f), vmin);
-                    tile[s1_byte_in_half(c, f)] = (uint8_t)sb;
+                    sts_u8(at, sb);
                     if (kDebug) p.hidden_steps[((size_t)b * p.steps + t0 + c) * F + f] = (uint8_t)sb;
                 }
                 for (int c = nc; c < kChunk; ++c) tile[s1_byte_in_half(c, f)] = 0;   // ragged last tile
@@ -381,14 +419,13 @@ __global__ void __launch_bounds__(1024, 1) feature_raster_kernel(RasterParams p)
 static size_t raster_smem_bytes(const SnnHandle *h)
 {
     const int Ipad = (h->I + 31) & ~31;
-    size_t off = ((size_t)h->I * h->F * 8 + (size_t)h->T * h->I + 15) & ~(size_t)15;
-    return off + (size_t)kRasterSlots * kChunk * Ipad + (size_t)kRasterSlots * kChunk * 4 +
+    return (((size_t)h->I * h->F * 8 + 15) & ~(size_t)15) + (size_t)kRasterSlots * kChunk * Ipad * 2 + (size_t)kRasterSlots * kChunk * 4 +
            (size_t)kRasterSlots * kChunk * h->Fp;
 }
 
 static bool raster_path_ok(const SnnHandle *h)
 {
-    return h->Uq && h->thr == 1.0f && !h->v0_dirty && h->I <= 256 &&
+    return h->Uq && h->thr == 1.0f && !h->v0_dirty && (size_t)h->I * h->F <= 65535 &&
            h->Fp * kRasterSlots <= 1024 && raster_smem_bytes(h) <= 227 * 1024;
 }
 
