@@ -215,12 +215,11 @@ def main():
     def step_resident():
         return pipe.step(frames=frames_dev, gt_center=gt_center, gt_tol=2)
 
-    stage = torch.empty_like(frames_dev)
-
     def step_e2e():
-        stage.copy_(frames_host, non_blocking=True)                     # H2D of this step's input
-        out = pipe.step(frames=stage, gt_center=gt_center, gt_tol=2)
-        res = torch.cat([out["hits"], out["n_valid"]]).cpu()             # D2H of the step's result
+        # public API fed from pinned host memory: H2D of this step's frames (side stream; the copy for the
+        # following step is started behind this step's kernels) ... D2H of the step's result
+        out = pipe.step_host(frames_host, gt_center=gt_center, gt_tol=2, next_frames=frames_host)
+        res = torch.cat([out["hits"], out["n_valid"]]).cpu()
         idx = out["top_idx"].cpu()
         return res, idx
 

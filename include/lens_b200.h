@@ -118,6 +118,12 @@ int lens_snn_get_timing(void *handle, float *feature_ms, float *output_ms, int64
 int lens_snn_forward(void *handle, const uint8_t *pooled, int B, int Q, float *counts,
                      uint8_t *hidden_steps, uint8_t *out_steps, int mode, void *stream);
 
+/* Same for the sub-range [b0, b0 + nb) of the handle's streams (pooled / counts / debug buffers start
+ * at stream b0): lets a caller pipeline host->device copies of one group of streams with the
+ * computation of the previous group.  b0 must be even (streams are tiled in pairs). */
+int lens_snn_forward_range(void *handle, const uint8_t *pooled, int b0, int nb, int Q, float *counts,
+                           uint8_t *hidden_steps, uint8_t *out_steps, int mode, void *stream);
+
 /* Operator seam `sinabs_model(x)` (lens/run_model.py:238) for an arbitrary float
  * raster: x [B][steps][I] f32 (already pooled), spikes_out [B][steps][P] f32.     */
 int lens_snn_forward_float(void *handle, const float *x, int B, int steps, float *spikes_out,

@@ -35,6 +35,7 @@ def _declare(L):
         "lens_snn_get_state": (i32, [vp, vp, vp, vp, vp]),
         "lens_snn_get_overflow": (i32, [vp, vp, vp]),
         "lens_snn_forward": (i32, [vp, vp, i32, i32, vp, vp, vp, i32, vp]),
+        "lens_snn_forward_range": (i32, [vp, vp, i32, i32, i32, vp, vp, vp, i32, vp]),
         "lens_snn_forward_float": (i32, [vp, vp, i32, i32, vp, vp]),
         "lens_seqmatch_topk": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]),
         "lens_recall": (i32, [vp, i32, i32, i32, i32, vp, i64, vp, i32, pi32, i32, vp, vp, vp]),

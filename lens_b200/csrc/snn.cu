@@ -585,7 +585,7 @@ static size_t scratch_budget() { return (size_t)6 << 30; }
 
 static int forward_common(SnnHandle *h, const uint8_t *pooled, const float *xin, int B, int steps,
                           float *counts, float *spikes_out, uint8_t *hidden_steps,
-                          uint8_t *out_steps, int mode, cudaStream_t st)
+                          uint8_t *out_steps, int mode, cudaStream_t st, int first_stream = 0)
 {
     const size_t per_pair = (size_t)ceil_div(steps, kTileSteps) * s1_tile_bytes(h->Fp);
     // streams are processed in groups (even size: a pair tile never straddles two groups)
@@ -602,22 +602,23 @@ static int forward_common(SnnHandle *h, const uint8_t *pooled, const float *xin,
         rc = snn_tc_prepare(h, st);
         if (rc) return rc;
     }
-    for (int b0 = 0; b0 < B; b0 += group) {
-        const int nb = std::min(group, B - b0);
-        uint8_t *hs = hidden_steps ? hidden_steps + (size_t)b0 * steps * h->F : nullptr;
+    for (int bl = 0; bl < B; bl += group) {
+        const int nb = std::min(group, B - bl);
+        const int b0 = first_stream + bl;   // index into the handle's state arrays
+        uint8_t *hs = hidden_steps ? hidden_steps + (size_t)bl * steps * h->F : nullptr;
         if (pooled && raster_path_ok(h))
-            rc = launch_feature_raster(h, pooled + (size_t)b0 * Q * h->I, b0, nb, steps, hs, st);
+            rc = launch_feature_raster(h, pooled + (size_t)bl * Q * h->I, b0, nb, steps, hs, st);
         else
-            rc = launch_feature(h, pooled ? pooled + (size_t)b0 * Q * h->I : nullptr,
-                                xin ? xin + (size_t)b0 * steps * h->I : nullptr, b0, nb, steps, hs, st);
+            rc = launch_feature(h, pooled ? pooled + (size_t)bl * Q * h->I : nullptr,
+                                xin ? xin + (size_t)bl * steps * h->I : nullptr, b0, nb, steps, hs, st);
         if (rc) return rc;
-        float *c = counts ? counts + (size_t)b0 * Q * h->P : nullptr;
-        uint8_t *os = out_steps ? out_steps + (size_t)b0 * steps * h->P : nullptr;
+        float *c = counts ? counts + (size_t)bl * Q * h->P : nullptr;
+        uint8_t *os = out_steps ? out_steps + (size_t)bl * steps * h->P : nullptr;
         if (use_tc)
             rc = snn_tc_output(h, h->S1, nb, b0, steps, c, os, st);
         else
             rc = launch_output_simt(h, b0, nb, steps, c,
-                                    spikes_out ? spikes_out + (size_t)b0 * steps * h->P : nullptr, os, st);
+                                    spikes_out ? spikes_out + (size_t)bl * steps * h->P : nullptr, os, st);
         if (rc) return rc;
     }
     return 0;
@@ -741,6 +742,24 @@ extern "C" int lens_snn_forward(void *handle, const uint8_t *pooled, int B, int 
     LENS_CHECK_ARG((int64_t)Q * h->T <= 2147483647LL, "lens_snn_forward: too many steps");
     return forward_common(h, pooled, nullptr, B, Q * h->T, counts, nullptr, hidden_steps, out_steps,
                           mode, as_stream(stream));
+}
+
+extern "C" int lens_snn_forward_range(void *handle, const uint8_t *pooled, int b0, int nb, int Q,
+                                      float *counts, uint8_t *hidden_steps, uint8_t *out_steps, int mode,
+                                      void *stream)
+{
+    LENS_CHECK_ARG(handle, "lens_snn_forward_range: NULL handle");
+    SnnHandle *h = static_cast<SnnHandle *>(handle);
+    LENS_CHECK_ARG(h->U != nullptr, "lens_snn_forward_range: handle was created without the raster matrix U");
+    LENS_CHECK_ARG(b0 >= 0 && nb >= 0 && Q >= 0 && b0 + nb <= h->maxB,
+                   "lens_snn_forward_range: streams [%d, %d) exceed max_streams=%d", b0, b0 + nb, h->maxB);
+    LENS_CHECK_ARG((b0 & 1) == 0, "lens_snn_forward_range: b0 must be even");
+    LENS_CHECK_ARG(mode >= LENS_SNN_AUTO && mode <= LENS_SNN_TC, "lens_snn_forward_range: bad mode %d", mode);
+    if (nb == 0 || Q == 0) return 0;
+    LENS_CHECK_ARG(pooled && counts, "lens_snn_forward_range: NULL buffer");
+    LENS_CHECK_ARG((int64_t)Q * h->T <= 2147483647LL, "lens_snn_forward_range: too many steps");
+    return forward_common(h, pooled, nullptr, nb, Q * h->T, counts, nullptr, hidden_steps, out_steps, mode,
+                          as_stream(stream), b0);
 }
 
 extern "C" int lens_snn_forward_float(void *handle, const float *x, int B, int steps,

@@ -146,6 +146,20 @@ class B200Network:
                                           int(mode), stream_ptr()), "lens_snn_forward")
         return (counts, hid, out) if want_steps else counts
 
+    def run_streams_range(self, pooled, b0, counts, mode=MODE_AUTO):
+        """Streams [b0, b0 + nb) only: pooled u8 [nb, Q, I] -> counts f32 [nb, Q, P] (pre-allocated).
+
+        Used to overlap the host->device copy of one group of streams with the compute of another;
+        the handle must already be sized for all streams (`ensure_streams`)."""
+        require_cuda(pooled, counts)
+        nb, Q, _ = pooled.shape
+        check(_lib.lib().lens_snn_forward_range(self._h, ptr(pooled), int(b0), int(nb), int(Q), ptr(counts),
+                                                None, None, int(mode), stream_ptr()), "lens_snn_forward_range")
+        return counts
+
+    def ensure_streams(self, B):
+        self._ensure_streams(B)
+
     def state(self):
         """(v0 [B, I], v1 [B, F], v2 [B, P]) membrane potentials."""
         B = self.max_streams

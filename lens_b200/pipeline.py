@@ -54,6 +54,45 @@ class InferencePipeline:
             out["hits"], out["n_valid"] = packed[:-1], packed[-1:]
         return out
 
+    def step_host(self, frames_host, gt_dense=None, gt_center=None, gt_tol=0, next_frames=None, reduce=True):
+        """The same step fed from PINNED HOST frames u8 [B, Q, roi, roi].
+
+        The host->device copy runs on a side stream into one of two staging buffers.  Passing the
+        following step's host tensor as `next_frames` starts its copy right after this step's kernels
+        are queued, so in a stream of steps the PCIe transfer of step k+1 hides behind the compute of
+        step k (every step still pays for its own copy; only the first one is exposed)."""
+        net, dev = self.net, self.device
+        main = torch.cuda.current_stream(dev)
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._stage, self._stage_free, self._pending = [None, None], [None, None], {}
+            self._slot = 0
+
+        def start_copy(src):
+            slot = self._slot
+            self._slot ^= 1
+            if self._stage[slot] is None or self._stage[slot].shape != src.shape:
+                self._stage[slot] = torch.empty(src.shape, dtype=torch.uint8, device=dev)
+            with torch.cuda.stream(self._copy_stream):
+                if self._stage_free[slot] is not None:
+                    self._copy_stream.wait_event(self._stage_free[slot])   # last reader of this buffer
+                self._stage[slot].copy_(src, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+            self._pending[src.data_ptr()] = (slot, ev)
+
+        if frames_host.data_ptr() not in self._pending:
+            start_copy(frames_host)
+        slot, ev = self._pending.pop(frames_host.data_ptr())
+        main.wait_event(ev)
+        out = self.step(frames=self._stage[slot], gt_dense=gt_dense, gt_center=gt_center, gt_tol=gt_tol,
+                        reduce=reduce)
+        self._stage_free[slot] = torch.cuda.Event()
+        self._stage_free[slot].record(main)
+        if next_frames is not None:
+            start_copy(next_frames)
+        return out
+
     @staticmethod
     def recall(hits, n_valid):
         nv = int(n_valid.item())

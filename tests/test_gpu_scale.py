@@ -104,3 +104,34 @@ def test_topn_invariants_large(B, Q, P, L):
         # numpy float32 / int is an IEEE division (torch's CUDA scalar division multiplies by 1/L)
         want = np.float32(sum(float(S[b, q + j, r + j]) for j in range(L))) / np.float32(L)
         assert float(D[b, r, q]) == float(want)
+
+
+def test_host_fed_step_equals_resident_step():
+    """step_host (pinned host frames, prefetched on a side stream) == step (resident frames)."""
+    from lens_b200.pipeline import InferencePipeline
+    B, Q, P, L = 50, 3, 1000, 2
+    Wf, Wo = synth.weights(100, 200, P, seed=1)
+    frames = torch.from_numpy(synth.frames(B, Q, 80, seed=2))
+    gt = cuda(synth.gt_centers(B, Q - L + 1, P - L + 1))
+    a = InferencePipeline(torch.from_numpy(Wf), torch.from_numpy(Wo), roi=80, k=8, T=250, L=L, max_streams=B)
+    b = InferencePipeline(torch.from_numpy(Wf), torch.from_numpy(Wo), roi=80, k=8, T=250, L=L, max_streams=B)
+    host = frames.pin_memory()
+    for _ in range(2):       # second round: state carry-over + buffer reuse
+        ra = a.step(frames=frames.cuda(), gt_center=gt, gt_tol=2)
+        rb = b.step_host(host, gt_center=gt, gt_tol=2, next_frames=host)
+        assert torch.equal(ra["S"], rb["S"])
+        assert torch.equal(ra["top_idx"], rb["top_idx"]) and torch.equal(ra["hits"], rb["hits"])
+
+
+def test_forward_range_equals_full_forward():
+    """lens_snn_forward_range over [0,20) + [20,50) == one lens_snn_forward over all 50 streams."""
+    B, Q, P = 50, 2, 1000
+    pooled = cuda(synth.pixel_counts((B, Q, 100), seed=9))
+    a, b = make_net(P, B), make_net(P, B)
+    full = a.run_streams(pooled=pooled, mode=2)
+    parts = torch.empty_like(full)
+    b.run_streams_range(pooled[:20].contiguous(), 0, parts[:20], mode=2)
+    b.run_streams_range(pooled[20:].contiguous(), 20, parts[20:], mode=2)
+    assert torch.equal(full, parts)
+    for x, y in zip(a.state(), b.state()):
+        assert torch.equal(x, y)
