@@ -13,18 +13,24 @@
 //
 // Mapping: M = 128 places (TMEM lanes), N = 64 columns = 32 consecutive timesteps of TWO streams
 // (columns 0..31 even stream, 32..63 odd stream), K = F padded to 32.  Time runs along the columns,
-// so an epilogue thread owns one (place, stream) and scans its 32 columns serially with the membrane
-// potential and spike count in registers -- the recurrence never leaves the register file for a
-// whole stream.  A CTA owns one place tile for the whole launch: its 6 digit planes (6 x 128 x Fp
-// bytes, canonical no-swizzle K-major core-matrix layout) stay resident in shared memory; hidden-
-// spike pair tiles (64 x Fp bytes, written by feature_kernel directly in the canonical layout)
-// stream in through a cp.async.bulk (TMA) ring.  The 6 x 64-column int32 accumulator set lives in
-// TMEM; the two epilogue warpgroups (one per stream of the pair) drain it into registers as three
-// 16+16-bit partial sums per step (tcgen05.ld), hand it back to the MMA warp at once and do the
-// recombination + IAF arithmetic from registers while the next tile's MMAs run.
+// so a thread owns one place and scans the columns of a stream serially with the membrane potential
+// and spike count in registers -- the recurrence never leaves the register file for a whole stream.
+// A CTA owns one place tile for the whole launch: its 6 digit planes (6 x 128 x Fp bytes, canonical
+// no-swizzle K-major core-matrix layout) stay resident in shared memory; hidden-spike pair tiles
+// (64 x Fp bytes, written by the feature kernel directly in the canonical layout) stream in through
+// a cp.async.bulk (TMA) ring.  TMEM holds the 6 x 64-column int32 accumulator set plus two 64-column
+// fp32 exchange buffers (512 columns in total).
 //
-// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue of
-// the even stream, warps 6..9 = epilogue of the odd stream.
+// Three warpgroups, registers redistributed with setmaxnreg:
+//   control  warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (warps 2-3 idle),
+//   drain    warps 4-7: tcgen05.ld the accumulators plane pair by plane pair (each pair goes back to the
+//            MMA warp as soon as it is read), recombine X = sum_j P_j 256^j in int64, round once to fp32,
+//            scale, tcgen05.st the 64 contraction results of every place into an exchange buffer,
+//   scan     warps 8-11: tcgen05.ld the results and run the serial IAF#2 recurrence of BOTH streams of the
+//            pair as two interleaved dependency chains (FADD -> FSET -> FADD -> FMNMX -> FADD per step),
+//            spike counts per query.
+// The serial chain (~830 cycles per tile) and the parallel drain/convert work (~900 cycles) thus overlap
+// with each other and with the MMAs of the next tile (~1950 cycles, shared-memory operand bound).
 #include "snn.cuh"
 
 #include <algorithm>
@@ -36,8 +42,12 @@ namespace tc {
 constexpr int kM = 128;                 // places per CTA tile
 constexpr int kN = kTileRows;           // TMEM columns per plane: 2 streams x 32 timesteps
 constexpr int kStages = 3;              // hidden-spike pair tiles in flight
-constexpr int kTmemCols = 512;          // allocation (power of two >= kPlanes * kN = 384)
-constexpr int kThreads = 320;
+constexpr int kTmemCols = 512;          // 6 planes x 64 accumulator columns + 2 x 64 exchange columns
+constexpr int kXCol = kPlanes * kN;     // first exchange column
+constexpr int kThreads = 384;           // 3 warpgroups
+constexpr int kRegsControl = 56;        // setmaxnreg budgets: 128 * (56 + 224 + 152) <= 384 * 168
+constexpr int kRegsDrain = 224;
+constexpr int kRegsScan = 152;
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
     return (uint32_t)__cvta_generic_to_shared(p);
@@ -135,6 +145,26 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, int32_t (&r)[32])
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
 }
+// store 16 consecutive 32-bit columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&r)[16])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
+        "%14, %15, %16};"
+        ::"r"(taddr), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]), "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7]),
+          "f"(r[8]), "f"(r[9]), "f"(r[10]), "f"(r[11]), "f"(r[12]), "f"(r[13]), "f"(r[14]), "f"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16f(uint32_t taddr, float (&r)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
+        "%14, %15}, [%16];"
+        : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]),
+          "=f"(r[8]), "=f"(r[9]), "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15])
+        : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, no-swizzle shared-memory operand descriptor (cute::UMMA::SmemDescriptor, version 1):
@@ -204,7 +234,9 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
     uint64_t *b_empty = b_full + kStages;                    // [kStages]
     uint64_t *acc_full = b_empty + kStages;                  // [3] one per plane pair
     uint64_t *acc_empty = acc_full + 3;                      // [3]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 3);
+    uint64_t *x_full = acc_empty + 3;                        // [2] exchange buffers drain -> scan
+    uint64_t *x_empty = x_full + 2;                          // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(x_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x;          // place tile
@@ -215,8 +247,9 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
         for (int i = 0; i < kStages; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
         for (int i = 0; i < 3; ++i) {
             mbar_init(acc_full + i, 1);
-            mbar_init(acc_empty + i, 8);  // one arrival per epilogue warp
+            mbar_init(acc_empty + i, 4);  // one arrival per drain warp
         }
+        for (int i = 0; i < 2; ++i) { mbar_init(x_full + i, 4); mbar_init(x_empty + i, 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {   // TMEM allocation (whole warp), address lands in shared memory
@@ -230,6 +263,8 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsControl));
     if (warp == 0) {
         // ===================== TMA producer (warp-uniform, one elected lane issues) ==============
         if (elect_one()) {
@@ -270,140 +305,204 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
                 // The accumulator set is handed over in plane pairs: the MMAs of pair g of this tile
                 // start as soon as the epilogue has drained pair g of the previous tile, and the
                 // epilogue starts draining pair g while pairs g+1.. are still being computed.
-#pragma unroll
+#pragma unroll 1
                 for (int g = 0; g < 3; ++g) {
                     mbar_wait(acc_empty + g, (it & 1) ^ 1);
                     tc_fence_after();
                     if (elect_one()) {
+                        // the two planes of the pair are interleaved along K so that consecutive MMAs
+                        // accumulate into different TMEM tiles (no back-to-back accumulator dependency)
+                        const uint64_t da_a = da0 + (uint32_t)(2 * g) * a_plane, da_b = da_a + a_plane;
+                        const uint32_t d_a = tmem_base + (2 * g) * kN, d_b = d_a + kN;
                         if (kKSteps > 0) {
 #pragma unroll
-                            for (int j = 2 * g; j < 2 * g + 2; ++j) {
-#pragma unroll
-                                for (int ks = 0; ks < kKSteps; ++ks)
-                                    mma_i8(tmem_base + j * kN, da0 + (uint32_t)(j * kM * kKSteps * 2 + ks * a_kstep),
-                                           db_s + ks * b_kstep, idesc, ks > 0 ? 1u : 0u);
+                            for (int ks = 0; ks < kKSteps; ++ks) {
+                                mma_i8(d_a, da_a + ks * a_kstep, db_s + ks * b_kstep, idesc, ks > 0 ? 1u : 0u);
+                                mma_i8(d_b, da_b + ks * a_kstep, db_s + ks * b_kstep, idesc, ks > 0 ? 1u : 0u);
                             }
                         } else {
-                            for (int j = 2 * g; j < 2 * g + 2; ++j)
-                                for (int ks = 0; ks < ksteps; ++ks)
-                                    mma_i8(tmem_base + j * kN, da0 + j * a_plane + ks * a_kstep, db_s + ks * b_kstep,
-                                           idesc, ks > 0 ? 1u : 0u);
+                            for (int ks = 0; ks < ksteps; ++ks) {
+                                mma_i8(d_a, da_a + ks * a_kstep, db_s + ks * b_kstep, idesc, ks > 0 ? 1u : 0u);
+                                mma_i8(d_b, da_b + ks * a_kstep, db_s + ks * b_kstep, idesc, ks > 0 ? 1u : 0u);
+                            }
                         }
-                        tc_commit(acc_full + g);               // this pair is ready for the epilogue
-                        if (g == 2) tc_commit(b_empty + stage); // smem slot reusable once all MMAs retire
+                        tc_commit(acc_full + g);               // this pair is ready for the drain warps
+                        // (every commit costs the tensor pipe ~150 cycles, so the shared-memory slot is
+                        //  released by the drain warpgroup when it sees the last pair complete)
                     }
                     __syncwarp();
                 }
                 __syncwarp();
             }
         }
-    } else {
-        // ===================== epilogue: IAF#2 scan, spike counts =====================
-        const int sp = (warp - 2) >> 2;                        // which stream of the pair
+    }
+    } else if (warp < 8) {
+        // ===================== drain warpgroup: TMEM accumulators -> exact fp32 contraction results ==========
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsDrain));
         const int quarter = warp & 3;                          // TMEM lanes this warp may touch
-        const int row = quarter * 32 + lane;
-        const int place = tile * kM + row;
+        const int place = tile * kM + quarter * 32 + lane;
+        const float scale = place < p.P ? p.scale[place] : 0.0f;
+        const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        const int my_pairs = (p.n_pairs - group + p.n_groups - 1) / p.n_groups;
+        const int total = my_pairs * p.chunks;
+        for (int it = 0; it < total; ++it) {
+            // X = sum_j P_j 256^j as (xh:xl) for the 64 columns of this lane
+            int32_t xl[kN], xh[kN];
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+                mbar_wait(acc_full + g, it & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int h = 0; h < kN / 16; ++h) {
+                    int32_t lo[16], hi[16];
+                    tmem_ld16(tlane + (2 * g) * kN + h * 16, lo);
+                    tmem_ld16(tlane + (2 * g + 1) * kN + h * 16, hi);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int n = 0; n < 16; ++n) {
+                        const int m = h * 16 + n;
+                        const int32_t qq = hi[n] * 256 + lo[n];          // |qq| < 2^30
+                        if (g == 0) {
+                            xl[m] = qq;
+                        } else if (g == 1) {
+                            const int64_t t = (int64_t)xl[m] + ((int64_t)qq << 16);
+                            xl[m] = (int32_t)(uint32_t)t;
+                            xh[m] = (int32_t)(t >> 32);
+                        } else {
+                            xh[m] += qq;
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(acc_empty + g);                  // pair g is free for the next tile's MMAs
+                    // all MMAs of this tile have retired: its spike tile may be overwritten by the TMA
+                    if (g == 2 && warp == 4) mbar_arrive(b_empty + (uint32_t)it % kStages);
+                }
+            }
+            // one rounding to fp32 (cvt.rn.f32.s64), exact power-of-two scale, hand over through TMEM
+            const uint32_t xb = it & 1;
+            mbar_wait(x_empty + xb, ((it >> 1) & 1) ^ 1);
+            tc_fence_after();
+#pragma unroll
+            for (int h = 0; h < kN / 16; ++h) {
+                float xf[16];
+#pragma unroll
+                for (int n = 0; n < 16; ++n) {
+                    const int m = h * 16 + n;
+                    xf[n] = __fmul_rn(__ll2float_rn((int64_t)(((uint64_t)(uint32_t)xh[m] << 32) | (uint32_t)xl[m])), scale);
+                }
+                tmem_st16(tlane + kXCol + xb * kN + h * 16, xf);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(x_full + xb);
+        }
+    } else {
+        // ===================== scan warpgroup: IAF#2 recurrence of both streams, spike counts ================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsScan));
+        const int quarter = warp & 3;
+        const int place = tile * kM + quarter * 32 + lane;
         const bool live_place = place < p.P;
-        const float scale = live_place ? p.scale[place] : 0.0f;
         const float thr = p.thr, vmin = p.vmin;
         const int Q = p.steps / p.T;
-        const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + sp * kTileSteps;
-        uint32_t it = 0;
-        for (int pr = group; pr < p.n_pairs; pr += p.n_groups) {
-            const int b = 2 * pr + sp;
-            const bool live = live_place && b < p.nb;
-            float v = live ? p.v2[(size_t)b * p.P + place] : 0.0f;
-            float count = 0.0f;
-            int t_in_q = 0, q = 0;
+        const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        const int my_pairs = (p.n_pairs - group + p.n_groups - 1) / p.n_groups;
+        int it = 0;
+        for (int pi = 0; pi < my_pairs; ++pi) {
+            const int pr = group + pi * p.n_groups;
+            const int b0 = 2 * pr, b1 = 2 * pr + 1;
+            const bool live0 = live_place && b0 < p.nb, live1 = live_place && b1 < p.nb;
+            float v0 = live0 ? p.v2[(size_t)b0 * p.P + place] : 0.0f;
+            float v1 = live1 ? p.v2[(size_t)b1 * p.P + place] : 0.0f;
+            float count0 = 0.0f, count1 = 0.0f;
+            int t_in_q = 0, q = 0;                               // both streams share the timeline
             for (int c = 0; c < p.chunks; ++c, ++it) {
-                // drain: three 16+16-bit partial sums per step, 96 registers; each plane pair is
-                // returned to the MMA warp as soon as it has been read
-                int32_t q0[kTileSteps], q1[kTileSteps], q2[kTileSteps];
+                const uint32_t xb = it & 1;
+                float x[kN];
+                mbar_wait(x_full + xb, (it >> 1) & 1);
+                tc_fence_after();
 #pragma unroll
-                for (int g = 0; g < 3; ++g) {
-                    mbar_wait(acc_full + g, it & 1);
-                    tc_fence_after();
+                for (int h = 0; h < kN / 16; ++h) {
+                    float t16[16];
+                    tmem_ld16f(tlane + kXCol + xb * kN + h * 16, t16);
+                    tmem_ld_wait();
 #pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        int32_t lo[16], hi[16];
-                        tmem_ld16(tbase + (2 * g) * kN + half * 16, lo);
-                        tmem_ld16(tbase + (2 * g + 1) * kN + half * 16, hi);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int n = 0; n < 16; ++n) {
-                            const int32_t qq = hi[n] * 256 + lo[n];
-                            if (g == 0) q0[half * 16 + n] = qq;
-                            else if (g == 1) q1[half * 16 + n] = qq;
-                            else q2[half * 16 + n] = qq;
-                        }
-                    }
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(acc_empty + g);   // pair g is free for the next tile's MMAs
+                    for (int n = 0; n < 16; ++n) x[h * 16 + n] = t16[n];
                 }
-                if (!live) continue;
-                // x[n] = RN_f32(sum_j P_j 256^j) * 2^q for the whole tile first: 32 independent
-                // chains (int64 recombination, one cvt.rn.f32.s64, one exact power-of-two scale)
-                float x[kTileSteps];
-#pragma unroll
-                for (int n = 0; n < kTileSteps; ++n) {
-                    const int64_t X = (int64_t)q0[n] + ((int64_t)q1[n] << 16) + ((int64_t)q2[n] << 32);
-                    x[n] = __fmul_rn(__ll2float_rn(X), scale);
-                }
-                // then the serial IAF#2 scan over the tile's timesteps
-                const int nvalid = min(kTileSteps, p.steps - c * kTileSteps);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(x_empty + xb);
+                if (!live0 && !live1) continue;
+
                 const int t_base = c * kTileSteps;
-                bool redo = true;
+                const int nvalid = min(kTileSteps, p.steps - t_base);
+                bool redo0 = live0, redo1 = live1;
                 if (kUnitThr && !kDebug && nvalid == kTileSteps && p.T >= kTileSteps) {
-                    // Fast path: at most one spike per step is assumed (checked; a tile that turns out
-                    // to hold a multi-spike step is redone below), which keeps the loop-carried chain at
-                    // FADD -> FSET -> FADD -> FMNMX -> FADD.  A query may end inside the tile: the spikes of
-                    // steps <= nb go to the ending query, the rest to the next one.
-                    const int nb = p.T - 1 - t_in_q;                 // tile-local index of the query's last step
-                    const float v_start = v;
-                    float cnt_all = 0.0f, cnt_head = 0.0f;
-                    bool multi = false;
+                    // Fast path: at most one spike per step is assumed (checked; a stream whose tile turns out
+                    // to hold a multi-spike step is redone below), which keeps each loop-carried chain at
+                    // FADD -> FSET -> FADD -> FMNMX -> FADD; the two streams give two independent chains.
+                    // A query may end inside the tile: the spikes of steps <= nb go to the ending query.
+                    const int nb = p.T - 1 - t_in_q;             // tile-local index of the query's last step
+                    const float s0 = v0, s1 = v1;
+                    float all0 = 0.0f, head0 = 0.0f, all1 = 0.0f, head1 = 0.0f;
+                    bool multi0 = false, multi1 = false;
 #pragma unroll
                     for (int n = 0; n < kTileSteps; ++n) {
-                        const float vv = __fadd_rn(v, x[n]);
-                        const float s = (vv >= 1.0f) ? 1.0f : 0.0f;
-                        const float cc = (vv >= 1.0f) ? 0.0f : 1.0f;  // 1 - s
-                        multi |= (vv >= 2.0f);
-                        v = __fadd_rn(fmaxf(__fadd_rn(vv, cc), 0.0f), -1.0f);
-                        cnt_all += s;
-                        if (n <= nb) cnt_head += s;
+                        const float a = __fadd_rn(v0, x[n]), b = __fadd_rn(v1, x[kTileSteps + n]);
+                        const float sa = (a >= 1.0f) ? 1.0f : 0.0f, sb = (b >= 1.0f) ? 1.0f : 0.0f;
+                        const float ca = (a >= 1.0f) ? 0.0f : 1.0f, cb = (b >= 1.0f) ? 0.0f : 1.0f;   // 1 - s
+                        multi0 |= (a >= 2.0f); multi1 |= (b >= 2.0f);
+                        v0 = __fadd_rn(fmaxf(__fadd_rn(a, ca), 0.0f), -1.0f);
+                        v1 = __fadd_rn(fmaxf(__fadd_rn(b, cb), 0.0f), -1.0f);
+                        all0 += sa; all1 += sb;
+                        if (n <= nb) { head0 += sa; head1 += sb; }
                     }
-                    if (!multi) {
-                        redo = false;
-                        if (nb < kTileSteps) {                        // the query ends in this tile
-                            p.counts[((size_t)b * Q + q) * p.P + place] = count + cnt_head;
-                            count = cnt_all - cnt_head;
-                            t_in_q = kTileSteps - 1 - nb;
-                            ++q;
-                        } else {
-                            count += cnt_all;
-                            t_in_q += kTileSteps;
-                        }
-                    } else {
-                        v = v_start;
-                    }
+                    const bool boundary = nb < kTileSteps;
+                    if (live0 && !multi0) {
+                        redo0 = false;
+                        if (boundary) { p.counts[((size_t)b0 * Q + q) * p.P + place] = count0 + head0; count0 = all0 - head0; }
+                        else count0 += all0;
+                    } else v0 = s0;
+                    if (live1 && !multi1) {
+                        redo1 = false;
+                        if (boundary) { p.counts[((size_t)b1 * Q + q) * p.P + place] = count1 + head1; count1 = all1 - head1; }
+                        else count1 += all1;
+                    } else v1 = s1;
                 }
-                if (redo) {   // generic: multi-spike steps, ragged last tile, debug output, tiny T
+                // generic: multi-spike steps, ragged last tile, debug output, tiny T, other thresholds
+                int tq0 = t_in_q, q0 = q;
+                if (redo0) {
 #pragma unroll
                     for (int n = 0; n < kTileSteps; ++n) {
                         if (n < nvalid) {
-                            const float s = iaf_out<kUnitThr>(v, x[n], thr, vmin);
-                            if (kDebug) p.out_steps[((size_t)b * p.steps + t_base + n) * p.P + place] = (uint8_t)fminf(s, 255.0f);
-                            count += s;
-                            if (++t_in_q == p.T) {
-                                p.counts[((size_t)b * Q + q) * p.P + place] = count;
-                                count = 0.0f; t_in_q = 0; ++q;
-                            }
+                            const float s = iaf_out<kUnitThr>(v0, x[n], thr, vmin);
+                            if (kDebug) p.out_steps[((size_t)b0 * p.steps + t_base + n) * p.P + place] = (uint8_t)fminf(s, 255.0f);
+                            count0 += s;
+                            if (++tq0 == p.T) { p.counts[((size_t)b0 * Q + q0) * p.P + place] = count0; count0 = 0.0f; tq0 = 0; ++q0; }
                         }
                     }
                 }
+                if (redo1) {
+                    int tq1 = t_in_q, q1 = q;
+#pragma unroll
+                    for (int n = 0; n < kTileSteps; ++n) {
+                        if (n < nvalid) {
+                            const float s = iaf_out<kUnitThr>(v1, x[kTileSteps + n], thr, vmin);
+                            if (kDebug) p.out_steps[((size_t)b1 * p.steps + t_base + n) * p.P + place] = (uint8_t)fminf(s, 255.0f);
+                            count1 += s;
+                            if (++tq1 == p.T) { p.counts[((size_t)b1 * Q + q1) * p.P + place] = count1; count1 = 0.0f; tq1 = 0; ++q1; }
+                        }
+                    }
+                }
+                // advance the shared timeline by the tile's valid steps
+                t_in_q += nvalid;
+                while (t_in_q >= p.T) { t_in_q -= p.T; ++q; }
             }
-            if (live) p.v2[(size_t)b * p.P + place] = v;
+            if (live0) p.v2[(size_t)b0 * p.P + place] = v0;
+            if (live1) p.v2[(size_t)b1 * p.P + place] = v1;
         }
     }
     tc_fence_before();
@@ -443,7 +542,7 @@ __global__ void __launch_bounds__(128) planes_kernel(const int64_t *__restrict__
 
 static size_t smem_bytes(int Fp)
 {
-    return (size_t)kPlanes * kM * Fp + (size_t)kStages * kN * Fp + (7 + 2 * kStages) * 8 + 16;
+    return (size_t)kPlanes * kM * Fp + (size_t)kStages * kN * Fp + (11 + 2 * kStages) * 8 + 16;
 }
 
 }  // namespace tc
