@@ -606,7 +606,9 @@ static int forward_common(SnnHandle *h, const uint8_t *pooled, const float *xin,
         const int nb = std::min(group, B - bl);
         const int b0 = first_stream + bl;   // index into the handle's state arrays
         uint8_t *hs = hidden_steps ? hidden_steps + (size_t)bl * steps * h->F : nullptr;
-        if (pooled && raster_path_ok(h))
+        if (pooled && use_tc && snn_tc_hidden_supported(h))
+            rc = snn_tc_hidden(h, pooled + (size_t)bl * Q * h->I, nb, b0, steps, hs, st);
+        else if (pooled && raster_path_ok(h))
             rc = launch_feature_raster(h, pooled + (size_t)bl * Q * h->I, b0, nb, steps, hs, st);
         else
             rc = launch_feature(h, pooled ? pooled + (size_t)bl * Q * h->I : nullptr,

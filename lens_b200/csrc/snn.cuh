@@ -46,8 +46,12 @@ struct SnnHandle {
     int8_t *S1 = nullptr;         // scratch hidden spikes [streams][steps][Fp]
     size_t S1_cap = 0;
     // tensor-core operands (built lazily by snn_tc.cu)
-    int8_t *Wo_planes = nullptr;  // [P_tiles][kPlanes][...] canonical UMMA layout
+    int8_t *Wo_planes = nullptr;  // [P_tiles][kPlanes][Fp/16][128][16] canonical UMMA layout
     int P_tiles = 0;
+    int8_t *Wf_planes = nullptr;  // [F_tiles][kPlanes][Ip/16][128][16]
+    int F_tiles = 0, Ip = 0;
+    int8_t *S0 = nullptr;         // scratch input-spike pair tiles [pairs][chunks][Ip/16][64][16]
+    size_t S0_cap = 0;
     int device = 0;
     // optional per-kernel timing (lens_snn_set_timing)
     struct TimedLaunch { cudaEvent_t start, stop; int kind; };   // kind 0 = feature, 1 = output
@@ -79,5 +83,8 @@ void snn_tc_release(SnnHandle *h);
 int snn_tc_output(SnnHandle *h, const int8_t *S1, int nb, int b0, int steps, float *counts,
                   uint8_t *out_steps, cudaStream_t st);
 bool snn_tc_supported(const SnnHandle *h);
+bool snn_tc_hidden_supported(const SnnHandle *h);
+int snn_tc_hidden(SnnHandle *h, const uint8_t *pooled, int nb, int b0, int steps, uint8_t *hidden_steps,
+                  cudaStream_t st);
 
 }  // namespace lens

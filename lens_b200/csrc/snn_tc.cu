@@ -192,10 +192,22 @@ struct Params {
     const float *scale;     // [P]
     float *v2;              // [nb][P] (offset to the first stream of the launch)
     float *counts;          // [nb][Q][P]
-    uint8_t *out_steps;     // nullable [nb][steps][P]
+    uint8_t *out_steps;     // nullable [nb][steps][P] (hidden layer: [nb][steps][P] hidden spikes)
     int P, Fp, T, steps, chunks, nb, n_pairs, n_groups;
     float thr, vmin;
+    // hidden-layer variant (kHidden): the "places" are feature neurons and the result is their spike
+    // raster, written as pair tiles for the output layer
+    int8_t *S1_out;         // [pairs][chunks][out_Fp/16][64][16]
+    int out_Fp;
+    int64_t *overflow;      // spike counts above LENS_MAX_SPIKE
 };
+
+__device__ __forceinline__ void bulk_s2g(void *gmem_dst, const void *smem_src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
+                 "r"(bytes)
+                 : "memory");
+}
 
 // One IAF#2 step on the exact contraction result.
 // kUnit: thr == 1 and v_min == -1 (the reference's fixed configuration, lens/run_model.py:151-156).
@@ -218,7 +230,8 @@ __device__ __forceinline__ float iaf_out(float &v, float x, float thr, float vmi
 
 // kKSteps = Fp / 32 as a compile-time constant (0 = generic runtime loop): with it the 6 x kKSteps
 // MMAs of a tile are straight-line code whose descriptors are constant offsets from two uniform bases.
-template <bool kUnitThr, bool kDebug, int kKSteps>
+// kHidden: feature layer (IAF#1) instead of output layer (IAF#2): spikes leave as pair tiles, no counts.
+template <bool kUnitThr, bool kDebug, int kKSteps, bool kHidden>
 __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -237,6 +250,7 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
     uint64_t *x_full = acc_empty + 3;                        // [2] exchange buffers drain -> scan
     uint64_t *x_empty = x_full + 2;                          // [2]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(x_empty + 2);
+    uint8_t *sOut = reinterpret_cast<uint8_t *>(bars) + 256;  // [2][8][64][16] spike staging (kHidden only)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x;          // place tile
@@ -410,6 +424,7 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
         const int Q = p.steps / p.T;
         const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
         const int my_pairs = (p.n_pairs - group + p.n_groups - 1) / p.n_groups;
+        long long n_over = 0;
         int it = 0;
         for (int pi = 0; pi < my_pairs; ++pi) {
             const int pr = group + pi * p.n_groups;
@@ -435,12 +450,18 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(x_empty + xb);
-                if (!live0 && !live1) continue;
+                if (!kHidden && !live0 && !live1) continue;
+                // hidden layer: this tile's spike bytes are staged in shared memory [kc][row = stream*32+n][16]
+                uint8_t *stage_out = sOut + (it & 1) * 8192 + (quarter * 2 + (lane >> 4)) * 1024 + (lane & 15);
+                if (kHidden) {
+                    if (warp == 8 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    asm volatile("bar.sync 1, 128;" ::: "memory");   // staging buffer (it & 1) is free again
+                }
 
                 const int t_base = c * kTileSteps;
                 const int nvalid = min(kTileSteps, p.steps - t_base);
                 bool redo0 = live0, redo1 = live1;
-                if (kUnitThr && !kDebug && nvalid == kTileSteps && p.T >= kTileSteps) {
+                if (kUnitThr && !kDebug && nvalid == kTileSteps && (kHidden || p.T >= kTileSteps)) {
                     // Fast path: at most one spike per step is assumed (checked; a stream whose tile turns out
                     // to hold a multi-spike step is redone below), which keeps each loop-carried chain at
                     // FADD -> FSET -> FADD -> FMNMX -> FADD; the two streams give two independent chains.
@@ -449,6 +470,23 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
                     const float s0 = v0, s1 = v1;
                     float all0 = 0.0f, head0 = 0.0f, all1 = 0.0f, head1 = 0.0f;
                     bool multi0 = false, multi1 = false;
+                    if (kHidden) {
+                        // Hidden layer: several spikes per step do occur (~3e-4 of neuron-steps), so the count is
+                        // computed exactly on the ALU in every step: for 0 <= m < 2^23, fl_rz(m + 2^23) - 2^23 is
+                        // trunc(m), and the low byte of fl_rz(m + 2^23) is the spike count itself.
+#pragma unroll
+                        for (int n = 0; n < kTileSteps; ++n) {
+                            const float a = __fadd_rn(v0, x[n]), b = __fadd_rn(v1, x[kTileSteps + n]);
+                            const float ta = __fadd_rz(fmaxf(a, 0.0f), 8388608.0f), tb = __fadd_rz(fmaxf(b, 0.0f), 8388608.0f);
+                            const float sa = __fsub_rn(ta, 8388608.0f), sb = __fsub_rn(tb, 8388608.0f);   // trunc, exact
+                            multi0 |= (a >= 128.0f); multi1 |= (b >= 128.0f);     // beyond LENS_MAX_SPIKE: generic path
+                            // v - s is exact, so relu(v - s + 1) - 1 rounds like the reference's three operations
+                            v0 = __fadd_rn(fmaxf(__fadd_rn(a, __fsub_rn(1.0f, sa)), 0.0f), -1.0f);
+                            v1 = __fadd_rn(fmaxf(__fadd_rn(b, __fsub_rn(1.0f, sb)), 0.0f), -1.0f);
+                            stage_out[n * 16] = (uint8_t)__float_as_uint(ta);
+                            stage_out[512 + n * 16] = (uint8_t)__float_as_uint(tb);
+                        }
+                    } else {
 #pragma unroll
                     for (int n = 0; n < kTileSteps; ++n) {
                         const float a = __fadd_rn(v0, x[n]), b = __fadd_rn(v1, x[kTileSteps + n]);
@@ -460,7 +498,13 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
                         all0 += sa; all1 += sb;
                         if (n <= nb) { head0 += sa; head1 += sb; }
                     }
+                    }
                     const bool boundary = nb < kTileSteps;
+                    if (kHidden) {
+                        redo0 = multi0; redo1 = multi1;
+                        if (multi0) v0 = s0;
+                        if (multi1) v1 = s1;
+                    } else {
                     if (live0 && !multi0) {
                         redo0 = false;
                         if (boundary) { p.counts[((size_t)b0 * Q + q) * p.P + place] = count0 + head0; count0 = all0 - head0; }
@@ -471,6 +515,9 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
                         if (boundary) { p.counts[((size_t)b1 * Q + q) * p.P + place] = count1 + head1; count1 = all1 - head1; }
                         else count1 += all1;
                     } else v1 = s1;
+                    }
+                } else if (kHidden) {
+                    redo0 = redo1 = true;
                 }
                 // generic: multi-spike steps, ragged last tile, debug output, tiny T, other thresholds
                 int tq0 = t_in_q, q0 = q;
@@ -478,7 +525,13 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
 #pragma unroll
                     for (int n = 0; n < kTileSteps; ++n) {
                         if (n < nvalid) {
-                            const float s = iaf_out<kUnitThr>(v0, x[n], thr, vmin);
+                            float s = iaf_out<kUnitThr>(v0, x[n], thr, vmin);
+                            if (kHidden) {
+                                if (s > (float)LENS_MAX_SPIKE) { s = (float)LENS_MAX_SPIKE; if (live0) ++n_over; }
+                                stage_out[n * 16] = (uint8_t)s;
+                                if (kDebug && live0) p.out_steps[((size_t)b0 * p.steps + t_base + n) * p.P + place] = (uint8_t)s;
+                                continue;
+                            }
                             if (kDebug) p.out_steps[((size_t)b0 * p.steps + t_base + n) * p.P + place] = (uint8_t)fminf(s, 255.0f);
                             count0 += s;
                             if (++tq0 == p.T) { p.counts[((size_t)b0 * Q + q0) * p.P + place] = count0; count0 = 0.0f; tq0 = 0; ++q0; }
@@ -490,7 +543,13 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
 #pragma unroll
                     for (int n = 0; n < kTileSteps; ++n) {
                         if (n < nvalid) {
-                            const float s = iaf_out<kUnitThr>(v1, x[kTileSteps + n], thr, vmin);
+                            float s = iaf_out<kUnitThr>(v1, x[kTileSteps + n], thr, vmin);
+                            if (kHidden) {
+                                if (s > (float)LENS_MAX_SPIKE) { s = (float)LENS_MAX_SPIKE; if (live1) ++n_over; }
+                                stage_out[512 + n * 16] = (uint8_t)s;
+                                if (kDebug && live1) p.out_steps[((size_t)b1 * p.steps + t_base + n) * p.P + place] = (uint8_t)s;
+                                continue;
+                            }
                             if (kDebug) p.out_steps[((size_t)b1 * p.steps + t_base + n) * p.P + place] = (uint8_t)fminf(s, 255.0f);
                             count1 += s;
                             if (++tq1 == p.T) { p.counts[((size_t)b1 * Q + q1) * p.P + place] = count1; count1 = 0.0f; tq1 = 0; ++q1; }
@@ -500,9 +559,27 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
                 // advance the shared timeline by the tile's valid steps
                 t_in_q += nvalid;
                 while (t_in_q >= p.T) { t_in_q -= p.T; ++q; }
+                if (kHidden) {
+                    for (int n = nvalid; n < kTileSteps; ++n) { stage_out[n * 16] = 0; stage_out[512 + n * 16] = 0; }
+                    // generic-proxy writes -> async proxy, then one thread ships the tile's rows of this
+                    // neuron tile (contiguous in the pair-tile layout) with one bulk store
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (warp == 8 && lane == 0) {
+                        const int kc0 = tile * 8, nkc = min(8, p.out_Fp / 16 - kc0);
+                        if (nkc > 0)
+                            bulk_s2g(p.S1_out + ((size_t)pr * p.chunks + c) * ((size_t)kN * p.out_Fp) + (size_t)kc0 * 1024,
+                                     sOut + (it & 1) * 8192, (uint32_t)nkc * 1024u);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                }
             }
             if (live0) p.v2[(size_t)b0 * p.P + place] = v0;
             if (live1) p.v2[(size_t)b1 * p.P + place] = v1;
+        }
+        if (kHidden) {
+            if (warp == 8 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            if (n_over) atomicAdd((unsigned long long *)p.overflow, (unsigned long long)n_over);
         }
     }
     tc_fence_before();
@@ -540,40 +617,100 @@ __global__ void __launch_bounds__(128) planes_kernel(const int64_t *__restrict__
     }
 }
 
-static size_t smem_bytes(int Fp)
+static size_t smem_bytes(int Fp, bool hidden = false)
 {
-    return (size_t)kPlanes * kM * Fp + (size_t)kStages * kN * Fp + (11 + 2 * kStages) * 8 + 16;
+    return (size_t)kPlanes * kM * Fp + (size_t)kStages * kN * Fp + 256 + (hidden ? 2 * 8192 : 0);
 }
 
 }  // namespace tc
+
+// Input-spike pair tiles for the hidden-layer kernel: S0[pair][chunk][Ip/16][64][16] int8 with
+// byte = (pixel > Uq[t][i]) -- the raster of lens/src/dataset.py:121 (see raster_thresholds_kernel).
+// One thread per 16-byte row segment (16 inputs of one step of one stream).
+__global__ void __launch_bounds__(256) raster_tiles_kernel(const uint8_t *__restrict__ pooled,
+                                                           const uint8_t *__restrict__ Uq, int I, int Ip, int T, int Q,
+                                                           int steps, int chunks, int nb, int n_pairs,
+                                                           int8_t *__restrict__ S0)
+{
+    const int vec_per_tile = Ip / 16 * kTileRows;
+    const long long total = (long long)n_pairs * chunks * vec_per_tile;
+    for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < total;
+         v += (long long)gridDim.x * blockDim.x) {
+        const long long tile_id = v / vec_per_tile;
+        const int r = (int)(v - tile_id * vec_per_tile);
+        const int kc = r / kTileRows, row = r - kc * kTileRows;
+        const int sp = row / kTileSteps, n = row - sp * kTileSteps;
+        const int pr = (int)(tile_id / chunks), c = (int)(tile_id - (long long)pr * chunks);
+        const int b = 2 * pr + sp, step = c * kTileSteps + n;
+        uint32_t out[4] = {0u, 0u, 0u, 0u};
+        if (b < nb && step < steps) {
+            const int q = step / T, t = step - q * T;
+            const uint8_t *px = pooled + ((size_t)b * Q + q) * I, *uq = Uq + (size_t)t * I;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                const int i = kc * 16 + e;
+                const uint32_t spike = (i < I && __ldg(px + i) > __ldg(uq + i)) ? 1u : 0u;
+                out[e >> 2] |= spike << (8 * (e & 3));
+            }
+        }
+        reinterpret_cast<uint4 *>(S0)[v] = make_uint4(out[0], out[1], out[2], out[3]);
+    }
+}
 
 bool snn_tc_supported(const SnnHandle *h)
 {
     return tc::smem_bytes(h->Fp) <= 227 * 1024;
 }
 
+// hidden layer on tensor cores: binary raster, IAF#0 at rest, reference configuration (thr 1, v_min -1)
+bool snn_tc_hidden_supported(const SnnHandle *h)
+{
+    const int Ip = (h->I + 31) & ~31;
+    return h->Uq && h->thr == 1.0f && h->vmin == -1.0f && !h->v0_dirty && Ip <= 256 &&
+           tc::smem_bytes(Ip, true) <= 227 * 1024;
+}
+
 int snn_tc_prepare(SnnHandle *h, cudaStream_t st)
 {
-    if (h->Wo_planes) return 0;
-    h->P_tiles = ceil_div(h->P, tc::kM);
-    const size_t bytes = (size_t)h->P_tiles * kPlanes * tc::kM * h->Fp;
-    LENS_CUDA(cudaMalloc(&h->Wo_planes, bytes));
-    dim3 grid(h->P_tiles, h->Fp / 16);
-    tc::planes_kernel<<<grid, 128, 0, st>>>(h->Wo_fx, h->F, h->P, h->Fp, h->Wo_planes);
-    LENS_LAUNCH_CHECK();
+    if (!h->Wo_planes) {
+        h->P_tiles = ceil_div(h->P, tc::kM);
+        const size_t bytes = (size_t)h->P_tiles * kPlanes * tc::kM * h->Fp;
+        LENS_CUDA(cudaMalloc(&h->Wo_planes, bytes));
+        dim3 grid(h->P_tiles, h->Fp / 16);
+        tc::planes_kernel<<<grid, 128, 0, st>>>(h->Wo_fx, h->F, h->P, h->Fp, h->Wo_planes);
+        LENS_LAUNCH_CHECK();
+    }
+    if (!h->Wf_planes && snn_tc_hidden_supported(h)) {
+        h->Ip = (h->I + 31) & ~31;
+        h->F_tiles = ceil_div(h->F, tc::kM);
+        const size_t bytes = (size_t)h->F_tiles * kPlanes * tc::kM * h->Ip;
+        LENS_CUDA(cudaMalloc(&h->Wf_planes, bytes));
+        dim3 grid(h->F_tiles, h->Ip / 16);
+        tc::planes_kernel<<<grid, 128, 0, st>>>(h->Wf_fx, h->I, h->F, h->Ip, h->Wf_planes);
+        LENS_LAUNCH_CHECK();
+    }
     return 0;
 }
 
 void snn_tc_release(SnnHandle *h)
 {
     if (h->Wo_planes) cudaFree(h->Wo_planes);
-    h->Wo_planes = nullptr;
+    if (h->Wf_planes) cudaFree(h->Wf_planes);
+    if (h->S0) cudaFree(h->S0);
+    h->Wo_planes = nullptr; h->Wf_planes = nullptr; h->S0 = nullptr; h->S0_cap = 0;
 }
+
+#define LENS_TC_LAUNCH_K(U, D, K, H)                                                                                 \
+    do {                                                                                                             \
+        LENS_CUDA(cudaFuncSetAttribute(tc::output_tc_kernel<U, D, K, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                       (int)smem));                                                                  \
+        tc::output_tc_kernel<U, D, K, H><<<grid, tc::kThreads, smem, st>>>(p);                                       \
+    } while (0)
 
 int snn_tc_output(SnnHandle *h, const int8_t *S1, int nb, int b0, int steps, float *counts,
                   uint8_t *out_steps, cudaStream_t st)
 {
-    tc::Params p;
+    tc::Params p{};
     p.planes = h->Wo_planes; p.S1 = S1; p.scale = h->Wo_scale;
     p.v2 = h->v2 + (size_t)b0 * h->P; p.counts = counts; p.out_steps = out_steps;
     p.P = h->P; p.Fp = h->Fp; p.T = h->T; p.steps = steps;
@@ -585,26 +722,60 @@ int snn_tc_output(SnnHandle *h, const int8_t *S1, int nb, int b0, int steps, flo
     dim3 grid(h->P_tiles, p.n_groups);
     LaunchTimer timer(h, st, 1);
     const bool unit = h->thr == 1.0f && h->vmin == -1.0f, dbg = out_steps != nullptr;
-#define LENS_TC_LAUNCH_K(U, D, K)                                                                                 \
-    do {                                                                                                          \
-        LENS_CUDA(cudaFuncSetAttribute(tc::output_tc_kernel<U, D, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                       (int)smem));                                                               \
-        tc::output_tc_kernel<U, D, K><<<grid, tc::kThreads, smem, st>>>(p);                                       \
-    } while (0)
-#define LENS_TC_LAUNCH(U, D)                                  \
-    do {                                                      \
-        if (h->Fp == 224) LENS_TC_LAUNCH_K(U, D, 7);          \
-        else if (h->Fp == 64) LENS_TC_LAUNCH_K(U, D, 2);      \
-        else LENS_TC_LAUNCH_K(U, D, 0);                       \
+#define LENS_TC_LAUNCH(U, D)                                     \
+    do {                                                         \
+        if (h->Fp == 224) LENS_TC_LAUNCH_K(U, D, 7, false);      \
+        else if (h->Fp == 64) LENS_TC_LAUNCH_K(U, D, 2, false);  \
+        else LENS_TC_LAUNCH_K(U, D, 0, false);                   \
     } while (0)
     if (unit && !dbg) LENS_TC_LAUNCH(true, false);
     else if (unit && dbg) LENS_TC_LAUNCH(true, true);
     else if (!unit && !dbg) LENS_TC_LAUNCH(false, false);
     else LENS_TC_LAUNCH(false, true);
-#undef LENS_TC_LAUNCH_K
 #undef LENS_TC_LAUNCH
     LENS_LAUNCH_CHECK();
     return 0;
 }
+
+// Feature layer on the tensor cores: raster tiles -> (W_feat digit planes) -> IAF#1 -> hidden-spike pair
+// tiles in h->S1.  Same kernel as the output layer with the kHidden epilogue.
+int snn_tc_hidden(SnnHandle *h, const uint8_t *pooled, int nb, int b0, int steps, uint8_t *hidden_steps,
+                  cudaStream_t st)
+{
+    const int chunks = ceil_div(steps, kTileSteps), n_pairs = (nb + 1) / 2;
+    const size_t s0_bytes = (size_t)n_pairs * chunks * kTileRows * h->Ip;
+    if (s0_bytes > h->S0_cap) {
+        if (h->S0) LENS_CUDA(cudaFree(h->S0));
+        h->S0 = nullptr; h->S0_cap = 0;
+        LENS_CUDA(cudaMalloc(&h->S0, s0_bytes));
+        h->S0_cap = s0_bytes;
+    }
+    {
+        const long long vecs = (long long)(s0_bytes / 16);
+        const int blocks = (int)std::min<long long>((vecs + 255) / 256, (long long)std::max(sm_count(), 1) * 16);
+        LaunchTimer timer(h, st, 0);
+        raster_tiles_kernel<<<blocks, 256, 0, st>>>(pooled, h->Uq, h->I, h->Ip, h->T, steps / h->T, steps, chunks, nb,
+                                                    n_pairs, h->S0);
+        LENS_LAUNCH_CHECK();
+    }
+    tc::Params p{};
+    p.planes = h->Wf_planes; p.S1 = h->S0; p.scale = h->Wf_scale;
+    p.v2 = h->v1 + (size_t)b0 * h->F; p.counts = nullptr; p.out_steps = hidden_steps;
+    p.P = h->F; p.Fp = h->Ip; p.T = h->T; p.steps = steps; p.chunks = chunks; p.nb = nb; p.n_pairs = n_pairs;
+    p.thr = h->thr; p.vmin = h->vmin;
+    p.S1_out = h->S1; p.out_Fp = h->Fp; p.overflow = h->counters;
+    const int sms = std::max(sm_count(), 1);
+    p.n_groups = std::max(1, std::min(p.n_pairs, sms / std::max(h->F_tiles, 1)));
+    const size_t smem = tc::smem_bytes(h->Ip, true);
+    dim3 grid(h->F_tiles, p.n_groups);
+    LaunchTimer timer(h, st, 0);
+    const bool dbg = hidden_steps != nullptr;
+    if (h->Ip == 128) { if (dbg) LENS_TC_LAUNCH_K(true, true, 4, true); else LENS_TC_LAUNCH_K(true, false, 4, true); }
+    else if (h->Ip == 64) { if (dbg) LENS_TC_LAUNCH_K(true, true, 2, true); else LENS_TC_LAUNCH_K(true, false, 2, true); }
+    else { if (dbg) LENS_TC_LAUNCH_K(true, true, 0, true); else LENS_TC_LAUNCH_K(true, false, 0, true); }
+    LENS_LAUNCH_CHECK();
+    return 0;
+}
+#undef LENS_TC_LAUNCH_K
 
 }  // namespace lens

@@ -44,19 +44,33 @@ __device__ __forceinline__ void ld16(uint32_t taddr, int32_t (&r)[16])
                    "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(taddr));
 }
 
+__device__ __forceinline__ void st16(uint32_t taddr, const float (&r)[16])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 ::"r"(taddr), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]), "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7]), "f"(r[8]), "f"(r[9]),
+                   "f"(r[10]), "f"(r[11]), "f"(r[12]), "f"(r[13]), "f"(r[14]), "f"(r[15]) : "memory");
+}
+__device__ __forceinline__ void ld16f(uint32_t taddr, float (&r)[16])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]), "=f"(r[8]), "=f"(r[9]),
+                   "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15]) : "r"(taddr));
+}
+
 template <int MODE>
-__global__ void __launch_bounds__(192, 1) bench(int tiles, long long *out, int *sink)
+__global__ void __launch_bounds__(320, 1) bench(int tiles, long long *out, int *sink)
 {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint64_t bars[8];   // full[3], empty[3], done
+    __shared__ uint64_t bars[12];   // full[3], empty[3], done, xfull[2], xempty[2]
     __shared__ uint32_t slot;
     constexpr int KS = 7, Fp = 224, N = 64;
     uint8_t *sA = smem, *sB = smem + 6 * 128 * Fp;
-    uint64_t *full = bars, *empty = bars + 3, *done = bars + 6;
+    uint64_t *full = bars, *empty = bars + 3, *done = bars + 6, *xfull = bars + 7, *xempty = bars + 9;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int i = 0; i < 3; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 4); }
         mbar_init(done, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(xfull + i, 4); mbar_init(xempty + i, 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -92,10 +106,11 @@ __global__ void __launch_bounds__(192, 1) bench(int tiles, long long *out, int *
         mbar_wait(done, 0);
         long long t1 = clock64();
         if (blockIdx.x == 0 && lane == 0) out[0] = t1 - t0;
-    } else if (warp >= 2 && MODE >= 1) {
+    } else if (warp >= 2 && warp < 6 && MODE >= 1) {
         const uint32_t tl = tm + ((uint32_t)((warp & 3) * 32) << 16);
         int acc = 0;
         for (int t = 0; t < tiles; ++t) {
+            int32_t xl[64], xh[64];
 #pragma unroll
             for (int g = 0; g < 3; ++g) {
                 if (MODE >= 2) { mbar_wait(full + g, t & 1); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -105,7 +120,15 @@ __global__ void __launch_bounds__(192, 1) bench(int tiles, long long *out, int *
                     ld16(tl + (2 * g) * N + h * 16, lo);
                     ld16(tl + (2 * g + 1) * N + h * 16, hi);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (MODE >= 3) {
+                    if (MODE >= 4) {
+#pragma unroll
+                        for (int n = 0; n < 16; ++n) {
+                            const int m = h * 16 + n; const int32_t qq = hi[n] * 256 + lo[n];
+                            if (g == 0) xl[m] = qq;
+                            else if (g == 1) { const int64_t tt = (int64_t)xl[m] + ((int64_t)qq << 16); xl[m] = (int32_t)(uint32_t)tt; xh[m] = (int32_t)(tt >> 32); }
+                            else xh[m] += qq;
+                        }
+                    } else if (MODE >= 3) {
 #pragma unroll
                         for (int n = 0; n < 16; ++n) acc += hi[n] * 256 + lo[n];
                     } else {
@@ -118,8 +141,60 @@ __global__ void __launch_bounds__(192, 1) bench(int tiles, long long *out, int *
                     if (lane == 0) mbar_arrive(empty + g);
                 }
             }
+            if (MODE >= 4) {
+                const uint32_t xb = t & 1;
+                if (MODE != 7 && MODE != 8) { mbar_wait(xempty + xb, ((t >> 1) & 1) ^ 1); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    float xf[16];
+#pragma unroll
+                    for (int n = 0; n < 16; ++n) {
+                        const int m = h * 16 + n;
+                        if (MODE == 6 || MODE == 8) xf[n] = __int_as_float(0x4B400000 + (xl[m] ^ xh[m])) - 12582912.0f;
+                        else xf[n] = __ll2float_rn((int64_t)(((uint64_t)(uint32_t)xh[m] << 32) | (uint32_t)xl[m])) * 0.5f;
+                    }
+                    if (MODE == 7 || MODE == 8) { acc += __float_as_int(xf[0] + xf[7] + xf[15] + xf[3] + xf[5] + xf[9] + xf[11] + xf[13] + xf[1] + xf[2] + xf[4] + xf[6] + xf[8] + xf[10] + xf[12] + xf[14]); }
+                    else st16(tl + 384 + xb * 64 + h * 16, xf);
+                }
+                if (MODE != 7 && MODE != 8) {
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(xfull + xb);
+                }
+            }
         }
         if (acc == 0x12345678) sink[0] = acc;
+    } else if (warp >= 6 && MODE >= 4 && MODE != 7 && MODE != 8) {
+        const uint32_t tl = tm + ((uint32_t)((warp & 3) * 32) << 16);
+        float v0 = 0.f, v1 = 0.f, c0 = 0.f, c1 = 0.f;
+        for (int t = 0; t < tiles; ++t) {
+            const uint32_t xb = t & 1;
+            float x[64];
+            mbar_wait(xfull + xb, (t >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                float t16[16];
+                ld16f(tl + 384 + xb * 64 + h * 16, t16);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int n = 0; n < 16; ++n) x[h * 16 + n] = t16[n];
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(xempty + xb);
+            if (MODE == 5) {
+#pragma unroll
+                for (int n = 0; n < 32; ++n) {
+                    const float a = v0 + x[n], b = v1 + x[32 + n];
+                    const float ca = a >= 1.f ? 0.f : 1.f, cb = b >= 1.f ? 0.f : 1.f;
+                    c0 += 1.f - ca; c1 += 1.f - cb;
+                    v0 = fmaxf(a + ca, 0.f) - 1.f; v1 = fmaxf(b + cb, 0.f) - 1.f;
+                }
+            } else { c0 += x[0] + x[63]; }
+        }
+        if (v0 + v1 + c0 + c1 == 12345.678f) sink[1] = 1;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -132,7 +207,7 @@ void run(const char *name, long long *d_out, int *sink)
     const int tiles = 2000;
     size_t smem = 6 * 128 * 224 + 64 * 224 + 1024;
     cudaFuncSetAttribute(bench<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    for (int rep = 0; rep < 2; ++rep) bench<MODE><<<148, 192, smem>>>(tiles, d_out, sink);
+    for (int rep = 0; rep < 2; ++rep) bench<MODE><<<148, 320, smem>>>(tiles, d_out, sink);
     cudaError_t e = cudaDeviceSynchronize();
     long long cyc = 0;
     cudaMemcpy(&cyc, d_out, sizeof(cyc), cudaMemcpyDeviceToHost);
@@ -147,5 +222,10 @@ int main()
     run<1>("+ free-running LDTM (4 warps)", d_out, sink);
     run<2>("+ pair full/empty barriers", d_out, sink);
     run<3>("+ integer combine per element", d_out, sink);
+    run<4>("+ int64 assemble, convert, STTM, scan WG loads x", d_out, sink);
+    run<5>("+ scan chains (2 streams)", d_out, sink);
+    run<6>("mode 4 with magic int32->float instead of I2F.S64", d_out, sink);
+    run<7>("mode 4 without STTM / x handoff", d_out, sink);
+    run<8>("mode 4 without I2F.S64 and without STTM", d_out, sink);
     return 0;
 }
