@@ -646,11 +646,19 @@ __global__ void __launch_bounds__(256) raster_tiles_kernel(const uint8_t *__rest
         if (b < nb && step < steps) {
             const int q = step / T, t = step - q * T;
             const uint8_t *px = pooled + ((size_t)b * Q + q) * I, *uq = Uq + (size_t)t * I;
+            if ((I & 3) == 0) {     // rows are 4-byte aligned: word loads + byte-wise SIMD compare
+                const uint32_t *px4 = reinterpret_cast<const uint32_t *>(px) + kc * 4;
+                const uint32_t *uq4 = reinterpret_cast<const uint32_t *>(uq) + kc * 4;
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-                const int i = kc * 16 + e;
-                const uint32_t spike = (i < I && __ldg(px + i) > __ldg(uq + i)) ? 1u : 0u;
-                out[e >> 2] |= spike << (8 * (e & 3));
+                for (int w = 0; w < 4; ++w)
+                    if (kc * 16 + 4 * w < I) out[w] = __vcmpgtu4(__ldg(px4 + w), __ldg(uq4 + w)) & 0x01010101u;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const int i = kc * 16 + e;
+                    const uint32_t spike = (i < I && __ldg(px + i) > __ldg(uq + i)) ? 1u : 0u;
+                    out[e >> 2] |= spike << (8 * (e & 3));
+                }
             }
         }
         reinterpret_cast<uint4 *>(S0)[v] = make_uint4(out[0], out[1], out[2], out[3]);
