@@ -153,8 +153,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb, ms = cpu_arm(args, seconds=max(20.0, 4.0 * (args.steps + args.warmup)), steps=args.steps,
-                     warmup=args.warmup)
+    budget = float(os.environ.get("LENS_BENCH_CPU_SECONDS", max(20.0, 4.0 * (args.steps + args.warmup))))
+    cb, ms = cpu_arm(args, seconds=budget, steps=args.steps, warmup=args.warmup)
     line = dict(metric="query_timesteps_per_sec", value=cb["value"], unit="query_timesteps/s",
                 n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=ms,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32+int64", data="synthetic",
@@ -163,7 +163,7 @@ def run_reference(args):
                          d2h_bytes_per_step=0),
                 note="reference = Python/sinabs (not installable offline); timed: the C oracle port of its "
                      "path on all host cores")
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(args, world):
@@ -177,8 +177,28 @@ def workload_config(args, world):
 
 
 # ------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Route everything libraries print to stdout (e.g. NCCL's version banner) to stderr so that the
+    ONE JSON line is the only thing on stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     args = parse()
+    quiet_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -319,7 +339,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"], _ = cpu_arm(args, seconds=args.cpu_seconds)
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
