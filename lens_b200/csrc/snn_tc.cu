@@ -193,7 +193,7 @@ struct Params {
     float *v2;              // [nb][P] (offset to the first stream of the launch)
     float *counts;          // [nb][Q][P]
     uint8_t *out_steps;     // nullable [nb][steps][P] (hidden layer: [nb][steps][P] hidden spikes)
-    int P, Fp, T, steps, chunks, nb, n_pairs, n_groups;
+    int P, Fp, T, steps, chunks, nb, n_pairs, n_tiles;
     float thr, vmin;
     // hidden-layer variant (kHidden): the "places" are feature neurons and the result is their spike
     // raster, written as pair tiles for the output layer
@@ -253,8 +253,11 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
     uint8_t *sOut = reinterpret_cast<uint8_t *>(bars) + 256;  // [2][8][64][16] spike staging (kHidden only)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = blockIdx.x;          // place tile
-    const int group = blockIdx.y;         // stream-pair group: pairs group, group + n_groups, ...
+    // Work items = (place tile, stream pair) in tile-major order; persistent CTAs take contiguous,
+    // equally sized ranges, so a CTA changes its place tile (and reloads the digit planes) at most a
+    // few times and every SM gets the same amount of work whatever P is.
+    const long long n_items = (long long)p.n_tiles * p.n_pairs;
+    const int item0 = (int)(n_items * blockIdx.x / gridDim.x), item1 = (int)(n_items * (blockIdx.x + 1) / gridDim.x);
 
     if (threadIdx.x == 0) {
         mbar_init(a_full, 1);
@@ -281,15 +284,24 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsControl));
     if (warp == 0) {
         // ===================== TMA producer (warp-uniform, one elected lane issues) ==============
-        if (elect_one()) {
-            mbar_expect_tx(a_full, kPlanes * plane_bytes);
-            const int8_t *src = p.planes + (size_t)tile * kPlanes * plane_bytes;
-            for (int j = 0; j < kPlanes; ++j)
-                bulk_g2s(sA + j * plane_bytes, src + (size_t)j * plane_bytes, plane_bytes, a_full);
-        }
-        __syncwarp();
         uint32_t it = 0;
-        for (int pr = group; pr < p.n_pairs; pr += p.n_groups) {
+        int cur_tile = -1;
+        for (int item = item0; item < item1; ++item) {
+            const int tile = item / p.n_pairs, pr = item - tile * p.n_pairs;
+            if (tile != cur_tile) {
+                // new place tile: every MMA that reads the old planes must have retired
+                if (cur_tile >= 0)
+                    for (uint32_t j = it > (uint32_t)kStages ? it - kStages : 0; j < it; ++j)
+                        mbar_wait(b_empty + j % kStages, (j / kStages) & 1);
+                if (elect_one()) {
+                    mbar_expect_tx(a_full, kPlanes * plane_bytes);
+                    const int8_t *src = p.planes + (size_t)tile * kPlanes * plane_bytes;
+                    for (int j = 0; j < kPlanes; ++j)
+                        bulk_g2s(sA + j * plane_bytes, src + (size_t)j * plane_bytes, plane_bytes, a_full);
+                }
+                __syncwarp();
+                cur_tile = tile;
+            }
             const int8_t *sb = p.S1 + (size_t)pr * p.chunks * tile_bytes;
             for (int c = 0; c < p.chunks; ++c, ++it) {
                 const uint32_t stage = it % kStages, phase = (it / kStages) & 1;
@@ -309,9 +321,11 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
         const uint64_t db0 = make_desc(smem_u32(sB), kN * 16, 128);
         const uint32_t a_plane = plane_bytes >> 4, a_kstep = (2 * kM * 16) >> 4;
         const uint32_t b_stage = tile_bytes >> 4, b_kstep = (2 * kN * 16) >> 4;
-        mbar_wait(a_full, 0);
-        uint32_t it = 0;
-        for (int pr = group; pr < p.n_pairs; pr += p.n_groups) {
+        uint32_t it = 0, a_phase = 0;
+        int cur_tile = -1;
+        for (int item = item0; item < item1; ++item) {
+            const int tile = item / p.n_pairs;
+            if (tile != cur_tile) { mbar_wait(a_full, a_phase); a_phase ^= 1; cur_tile = tile; }   // planes landed
             for (int c = 0; c < p.chunks; ++c, ++it) {
                 const uint32_t stage = it % kStages, phase = (it / kStages) & 1;
                 mbar_wait(b_full + stage, phase);           // spikes landed
@@ -354,12 +368,12 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
         // ===================== drain warpgroup: TMEM accumulators -> exact fp32 contraction results ==========
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsDrain));
         const int quarter = warp & 3;                          // TMEM lanes this warp may touch
-        const int place = tile * kM + quarter * 32 + lane;
-        const float scale = place < p.P ? p.scale[place] : 0.0f;
         const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        const int my_pairs = (p.n_pairs - group + p.n_groups - 1) / p.n_groups;
-        const int total = my_pairs * p.chunks;
-        for (int it = 0; it < total; ++it) {
+        int it = 0;
+        for (int item = item0; item < item1; ++item) {
+        const int place = (item / p.n_pairs) * kM + quarter * 32 + lane;
+        const float scale = place < p.P ? p.scale[place] : 0.0f;
+        for (int c = 0; c < p.chunks; ++c, ++it) {
             // X = sum_j P_j 256^j as (xh:xl) for the 64 columns of this lane
             int32_t xl[kN], xh[kN];
 #pragma unroll
@@ -414,20 +428,20 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
             __syncwarp();
             if (lane == 0) mbar_arrive(x_full + xb);
         }
+        }
     } else {
         // ===================== scan warpgroup: IAF#2 recurrence of both streams, spike counts ================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsScan));
         const int quarter = warp & 3;
-        const int place = tile * kM + quarter * 32 + lane;
-        const bool live_place = place < p.P;
         const float thr = p.thr, vmin = p.vmin;
         const int Q = p.steps / p.T;
         const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        const int my_pairs = (p.n_pairs - group + p.n_groups - 1) / p.n_groups;
         long long n_over = 0;
         int it = 0;
-        for (int pi = 0; pi < my_pairs; ++pi) {
-            const int pr = group + pi * p.n_groups;
+        for (int item = item0; item < item1; ++item) {
+            const int tile = item / p.n_pairs, pr = item - tile * p.n_pairs;
+            const int place = tile * kM + quarter * 32 + lane;
+            const bool live_place = place < p.P;
             const int b0 = 2 * pr, b1 = 2 * pr + 1;
             const bool live0 = live_place && b0 < p.nb, live1 = live_place && b1 < p.nb;
             float v0 = live0 ? p.v2[(size_t)b0 * p.P + place] : 0.0f;
@@ -725,9 +739,9 @@ int snn_tc_output(SnnHandle *h, const int8_t *S1, int nb, int b0, int steps, flo
     p.chunks = ceil_div(steps, kTileSteps); p.nb = nb; p.n_pairs = (nb + 1) / 2;
     p.thr = h->thr; p.vmin = h->vmin;
     const int sms = std::max(sm_count(), 1);
-    p.n_groups = std::max(1, std::min(p.n_pairs, sms / std::max(h->P_tiles, 1)));
+    p.n_tiles = h->P_tiles;
     const size_t smem = tc::smem_bytes(h->Fp);
-    dim3 grid(h->P_tiles, p.n_groups);
+    dim3 grid((unsigned)std::min<long long>(sms, (long long)h->P_tiles * p.n_pairs));
     LaunchTimer timer(h, st, 1);
     const bool unit = h->thr == 1.0f && h->vmin == -1.0f, dbg = out_steps != nullptr;
 #define LENS_TC_LAUNCH(U, D)                                     \
@@ -773,9 +787,9 @@ int snn_tc_hidden(SnnHandle *h, const uint8_t *pooled, int nb, int b0, int steps
     p.thr = h->thr; p.vmin = h->vmin;
     p.S1_out = h->S1; p.out_Fp = h->Fp; p.overflow = h->counters;
     const int sms = std::max(sm_count(), 1);
-    p.n_groups = std::max(1, std::min(p.n_pairs, sms / std::max(h->F_tiles, 1)));
+    p.n_tiles = h->F_tiles;
     const size_t smem = tc::smem_bytes(h->Ip, true);
-    dim3 grid(h->F_tiles, p.n_groups);
+    dim3 grid((unsigned)std::min<long long>(sms, (long long)h->F_tiles * p.n_pairs));
     LaunchTimer timer(h, st, 0);
     const bool dbg = hidden_steps != nullptr;
     if (h->Ip == 128) { if (dbg) LENS_TC_LAUNCH_K(true, true, 4, true); else LENS_TC_LAUNCH_K(true, false, 4, true); }
