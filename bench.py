@@ -52,6 +52,16 @@ def parse():
     return ap.parse_args()
 
 
+def load_traffic(kernel, workload):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (None if the workload differs)."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        t = json.load(open(path)).get(kernel)
+        return t["dram_bytes_per_launch"] if t and t["workload"] == workload else None
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -289,7 +299,9 @@ def main():
     achieved = total_flops / (ktime["output_ms"] / 1e3) / 1e12 if ktime["output_ms"] > 0 else 0.0
     roofline = dict(kernel="snn output layer (F->P contraction + IAF#2)", bound="tensor", achieved=achieved,
                     peak=peaks["bf16_sustained"], unit="TFLOP/s", frac=achieved / peaks["bf16_sustained"],
-                    traffic=None, peak_source=peaks["source"] + " bf16 sustained",
+                    traffic=load_traffic("output_tc_kernel", "streams=%d,queries=%d,places=%d,feature=%d" %
+                                         (B, Q, P, F)),
+                    peak_source=peaks["source"] + " bf16 sustained",
                     kernel_ms=out_ms, feature_kernel_ms=ktime["feature_ms"] / max(ktime["n_feature"], 1),
                     share_of_step=ktime["output_ms"] / sum(ms),
                     algorithmic="2*F*P FLOP per query timestep (output layer); 2*I*F more in the feature kernel")
@@ -332,7 +344,8 @@ def main():
                                events_per_gpu=n_tot, windows=n_win_tot, ms=bsec * 1e3,
                                roofline=dict(bound="hbm", achieved=alg_bytes / bsec / 1e9, peak=peaks["hbm_gbs"],
                                              unit="GB/s", frac=alg_bytes / bsec / 1e9 / peaks["hbm_gbs"],
-                                             traffic=None, peak_source=peaks["source"],
+                                             traffic=load_traffic("bin_kernel", "events=%d" % n_tot),
+                                             peak_source=peaks["source"],
                                              algorithmic="8 B/event + 1 B per frame pixel + I B per frame"))
         del t_dev, x_dev, y_dev
 

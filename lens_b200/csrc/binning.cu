@@ -139,6 +139,78 @@ __global__ void __launch_bounds__(512) bin_kernel(BinParams p)
     }
 }
 
+// Fast path: roi is a power of two (<= 256), no crop offset, one band.  Two events are processed per
+// 32-bit word of the x / y arrays: (c - shift) mod roi for both halves is (c + roi - shift) & (roi - 1)
+// with one add and one mask, the two 16-bit bin indices come from one shift-or, and a word takes the
+// per-event path only if one of its events lies outside the roi.  grid = n_win.
+__global__ void __launch_bounds__(512) bin_pow2_kernel(BinParams p, int log2roi)
+{
+    extern __shared__ uint32_t hist[];
+    __shared__ int s_kept;
+    const int64_t w = blockIdx.x;
+    const int roi = p.roi, nbins = roi * roi;
+    for (int i = threadIdx.x; i < nbins; i += blockDim.x) hist[i] = 0u;
+    if (threadIdx.x == 0) s_kept = 0;
+    __syncthreads();
+    const uint32_t m2 = (uint32_t)(roi - 1) * 0x00010001u;                  // per-half mask
+    const uint32_t add2 = (uint32_t)(roi - p.index_shift) * 0x00010001u;   // per-half (roi - shift)
+    const uint32_t oob2 = ~m2;
+    const int64_t e0 = p.win_offsets[w], e1 = p.win_offsets[w + 1];
+    int64_t a0 = (e0 + 7) & ~(int64_t)7;
+    if (a0 > e1) a0 = e1;
+    const int64_t a1 = a0 + ((e1 - a0) & ~(int64_t)7);
+    int kept = 0;
+    for (int64_t e = e0 + threadIdx.x; e < a0; e += blockDim.x) bin_one(p, hist, 0, roi, p.x[e], p.y[e], kept);
+    const uint4 *x8 = reinterpret_cast<const uint4 *>(p.x + a0);
+    const uint4 *y8 = reinterpret_cast<const uint4 *>(p.y + a0);
+    const int64_t n8 = (a1 - a0) >> 3;
+    for (int64_t j = threadIdx.x; j < n8; j += blockDim.x) {
+        const uint4 xv = __ldg(x8 + j), yv = __ldg(y8 + j);
+        const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w}, ys[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            if (((xs[h] | ys[h]) & oob2) == 0u) {            // both events inside the roi
+                const uint32_t cx = (xs[h] + add2) & m2, cy = (ys[h] + add2) & m2;
+                const uint32_t idx2 = (cy << log2roi) | cx;  // two bin indices, 16 bits each
+                atomicAdd(&hist[idx2 & 0xffffu], 1u);
+                atomicAdd(&hist[idx2 >> 16], 1u);
+                kept += 2;
+            } else {
+                bin_one(p, hist, 0, roi, xs[h] & 0xffff, ys[h] & 0xffff, kept);
+                bin_one(p, hist, 0, roi, xs[h] >> 16, ys[h] >> 16, kept);
+            }
+        }
+    }
+    for (int64_t e = a1 + threadIdx.x; e < e1; e += blockDim.x) bin_one(p, hist, 0, roi, p.x[e], p.y[e], kept);
+    if (p.win_events) {
+        for (int o = 16; o > 0; o >>= 1) kept += __shfl_xor_sync(0xffffffffu, kept, o);
+        if ((threadIdx.x & 31) == 0 && kept) atomicAdd(&s_kept, kept);
+    }
+    __syncthreads();
+    if (p.win_events && threadIdx.x == 0) p.win_events[w] = s_kept;
+    if (p.frames) {
+        uint32_t *f4 = reinterpret_cast<uint32_t *>(p.frames + w * (int64_t)nbins);
+        for (int i = threadIdx.x; i < (nbins >> 2); i += blockDim.x) {
+            uint32_t o = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                uint32_t v = hist[4 * i + b];
+                v = p.wrap_u8 ? (v & 255u) : min(v, 255u);
+                o |= v << (8 * b);
+            }
+            f4[i] = o;
+        }
+    }
+    if (p.pooled) {
+        const int I = p.dims * p.dims;
+        for (int o = threadIdx.x; o < I; o += blockDim.x) {
+            const int i = o / p.dims, j = o - i * p.dims;
+            const uint32_t v = hist[(p.k * i + p.c) * roi + (p.k * j + p.c)];
+            p.pooled[w * I + o] = (uint8_t)(p.wrap_u8 ? (v & 255u) : min(v, 255u));
+        }
+    }
+}
+
 __global__ void pool_kernel(const uint8_t *__restrict__ frames, int64_t n, int roi, int k, int dims,
                             int c, uint8_t *__restrict__ pooled)
 {
@@ -194,8 +266,16 @@ extern "C" int lens_bin_events(const uint32_t *t_us, const uint16_t *x, const ui
     size_t smem = (size_t)band_rows * roi * 4;
     LENS_CUDA(cudaFuncSetAttribute(bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)smem));
-    dim3 grid((unsigned)n_win, (unsigned)p.n_bands);
-    bin_kernel<<<grid, 512, smem, st>>>(p);
+    const bool pow2 = (roi & (roi - 1)) == 0 && roi >= 4 && roi <= 256;
+    if (pow2 && roi_x0 == 0 && roi_y0 == 0 && p.n_bands == 1 && index_shift <= 1) {
+        int log2roi = 0;
+        while ((1 << log2roi) < roi) ++log2roi;
+        LENS_CUDA(cudaFuncSetAttribute(bin_pow2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        bin_pow2_kernel<<<(unsigned)n_win, 512, smem, st>>>(p, log2roi);
+    } else {
+        dim3 grid((unsigned)n_win, (unsigned)p.n_bands);
+        bin_kernel<<<grid, 512, smem, st>>>(p);
+    }
     LENS_LAUNCH_CHECK();
     return 0;
 }

@@ -37,6 +37,8 @@ def make_events(rng, n, sensor, n_win, window, hot=True):
     (32, 32, 1, 0, 0, 0, False),      # k = 1, saturating
     (346, 260, 10, 40, 0, 1, True),   # DAVIS346-sized frame: multi-band histogram
     (16, 7, 1, 3, 2, 1, True),        # odd roi (unaligned frame rows)
+    (128, 64, 8, 0, 0, 1, True),      # power-of-two fast path with events outside the roi
+    (256, 256, 16, 0, 0, 1, False),   # largest fast-path roi, saturating
 ])
 def test_bin_events(sensor, roi, k, x0, y0, shift, wrap):
     from lens_b200 import ops
