@@ -13,6 +13,7 @@
 // over keys (orderable(value) << 32 | index).
 #include "common.cuh"
 
+#include <algorithm>
 #include <climits>
 
 namespace lens {
@@ -105,6 +106,82 @@ seqmatch_topk_kernel(const float *__restrict__ S, int Q, int P, int L, int N,
     }
 }
 
+// ---- warp-per-query variant (N <= 32) ------------------------------------------------------------
+// One warp scores one (stream, query): lane i of the warp holds the i-th largest key seen so far.
+// Candidates arrive 32 at a time (coalesced loads of the L diagonal terms); a batch is merged only if
+// one of its keys beats the current 32nd largest (warp vote), by a 32-element bitonic sort of the batch
+// and a bitonic merge with the running list -- shuffles only, no shared memory, no block barriers.
+__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int m)
+{
+    const unsigned lo = __shfl_xor_sync(0xffffffffu, (unsigned)v, m);
+    const unsigned hi = __shfl_xor_sync(0xffffffffu, (unsigned)(v >> 32), m);
+    return ((unsigned long long)hi << 32) | lo;
+}
+__device__ __forceinline__ unsigned long long shfl_u64(unsigned long long v, int src)
+{
+    const unsigned lo = __shfl_sync(0xffffffffu, (unsigned)v, src);
+    const unsigned hi = __shfl_sync(0xffffffffu, (unsigned)(v >> 32), src);
+    return ((unsigned long long)hi << 32) | lo;
+}
+
+__global__ void __launch_bounds__(256)
+seqmatch_topk_warp_kernel(const float *__restrict__ S, long long n_queries, int Q, int P, int L, int N,
+                          float *__restrict__ D_out, float *__restrict__ top_val, int32_t *__restrict__ top_idx)
+{
+    const int lane = threadIdx.x & 31;
+    const int Qo = Q - L + 1, Po = P - L + 1;
+    const float fl = (float)L;
+    const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long g = warp0; g < n_queries; g += n_warps) {
+        const int b = (int)(g / Qo), q = (int)(g - (long long)b * Qo);
+        const float *Sb = S + ((size_t)b * Q + q) * P;
+        unsigned long long best = 0ull;                    // lane i: i-th largest key, 0 = empty
+        for (int r0 = 0; r0 < Po; r0 += 32) {
+            const int r = r0 + lane;
+            unsigned long long key = 0ull;
+            if (r < Po) {
+                float acc = 0.0f;
+                for (int j = 0; j < L; ++j) acc += __ldg(Sb + (size_t)j * P + (r + j));
+                const float d = __fdiv_rn(acc, fl);
+                if (D_out) D_out[((size_t)b * Po + r) * Qo + q] = d;
+                key = ((unsigned long long)f32_orderable(d) << 32) | (uint32_t)r;
+            }
+            const unsigned long long kth = shfl_u64(best, 31);          // current 32nd largest
+            if (!__any_sync(0xffffffffu, key > kth)) continue;          // nothing in this batch can enter
+            // bitonic sort of the batch, descending
+#pragma unroll
+            for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    const unsigned long long other = shfl_xor_u64(key, j);
+                    const bool take_max = (((lane & j) == 0) == ((lane & k) == 0));
+                    key = take_max ? (key > other ? key : other) : (key < other ? key : other);
+                }
+            }
+            // top 32 of (running list U batch): elementwise max against the reversed batch is bitonic
+            const unsigned long long rev = shfl_u64(key, 31 - lane);
+            unsigned long long c = best > rev ? best : rev;
+#pragma unroll
+            for (int j = 16; j > 0; j >>= 1) {
+                const unsigned long long other = shfl_xor_u64(c, j);
+                c = ((lane & j) == 0) ? (c > other ? c : other) : (c < other ? c : other);
+            }
+            best = c;
+        }
+        if (lane < N) {
+            const size_t o = (size_t)g * N + lane;
+            if (best == 0ull) {
+                top_val[o] = -INFINITY;
+                top_idx[o] = -1;
+            } else {
+                top_val[o] = f32_from_orderable((uint32_t)(best >> 32));
+                top_idx[o] = (int32_t)(uint32_t)(best & 0xffffffffull);
+            }
+        }
+    }
+}
+
 struct RecallParams {
     const int32_t *top_idx;
     int B, Qo, Po, N;
@@ -175,9 +252,15 @@ extern "C" int lens_seqmatch_topk(const float *S, int B, int Q, int P, int L, in
     LENS_CHECK_ARG(B == 0 || (S && top_val && top_idx), "lens_seqmatch_topk: NULL buffer");
     LENS_CHECK_ARG((int64_t)B * (Q - L + 1) <= 2147483647LL, "lens_seqmatch_topk: too many (stream, query) pairs");
     if (B == 0) return 0;
-    dim3 grid((unsigned)((int64_t)B * (Q - L + 1)));
-    seqmatch_topk_kernel<<<grid, kMatchThreads, 0, as_stream(stream)>>>(S, Q, P, L, N, D_out, top_val,
-                                                                        top_idx);
+    const long long n_queries = (long long)B * (Q - L + 1);
+    if (N <= 32) {
+        const long long blocks = std::min<long long>((n_queries + 7) / 8, (long long)std::max(sm_count(), 1) * 16);
+        seqmatch_topk_warp_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(S, n_queries, Q, P, L, N, D_out,
+                                                                                  top_val, top_idx);
+    } else {
+        dim3 grid((unsigned)n_queries);
+        seqmatch_topk_kernel<<<grid, kMatchThreads, 0, as_stream(stream)>>>(S, Q, P, L, N, D_out, top_val, top_idx);
+    }
     LENS_LAUNCH_CHECK();
     return 0;
 }
