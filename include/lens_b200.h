@@ -153,6 +153,16 @@ int lens_recall(const int32_t *top_idx, int B, int Qo, int Po, int N, const uint
                 int64_t gt_stream_stride, const int32_t *gt_center, int gt_tol, const int *ns,
                 int n_ns, int64_t *hits, int64_t *n_valid, void *stream);
 
+/* Precision-recall counters of lens/src/metrics.py:21-139 (createPR, matching='single'), used by
+ * lens/run_model.py:319-327 with n_thresh = 100.  S and GT are [Po][Qo] (rows = database), exactly the
+ * matrices the reference passes (after its transposes).  Per query column the best match is the FIRST
+ * row attaining the maximum (np.argmax); thresholds are np.linspace(max, min, n_thresh) over the best
+ * similarities, evaluated in float64 like numpy.
+ *   tp, fp [n_thresh] i64 device: true / false positives with best >= threshold
+ *   gtp    [1] i64 device: number of queries that have a positive at all (GT.any(0))             */
+int lens_pr_counts(const float *S, const uint8_t *GT, int Po, int Qo, int n_thresh, int64_t *tp,
+                   int64_t *fp, int64_t *gtp, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

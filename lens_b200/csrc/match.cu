@@ -239,9 +239,75 @@ __global__ void __launch_bounds__(256) recall_kernel(RecallParams p)
     if (threadIdx.x == 0 && s_valid) atomicAdd(p.n_valid, (unsigned long long)s_valid);
 }
 
+// createPR, matching = 'single' (lens/src/metrics.py:21-139): one CTA, columns strided over threads.
+// best[q] / hit[q] live in shared memory (Qo <= 8192).
+__global__ void __launch_bounds__(256) pr_counts_kernel(const float *__restrict__ S, const uint8_t *__restrict__ GT,
+                                                        int Po, int Qo, int n_thresh,
+                                                        unsigned long long *__restrict__ tp,
+                                                        unsigned long long *__restrict__ fp,
+                                                        unsigned long long *__restrict__ gtp)
+{
+    extern __shared__ float s_best[];                       // [Qo] best similarity per query
+    uint8_t *s_hit = reinterpret_cast<uint8_t *>(s_best + Qo);   // [Qo] GT at the best match
+    __shared__ float s_max[8], s_min[8];
+    __shared__ unsigned int s_gtp;
+    if (threadIdx.x == 0) s_gtp = 0;
+    __syncthreads();
+    float vmax = -INFINITY, vmin = INFINITY;
+    unsigned int my_gtp = 0;
+    for (int q = threadIdx.x; q < Qo; q += blockDim.x) {
+        float best = -INFINITY;
+        int arg = 0;
+        bool any = false;
+        for (int r = 0; r < Po; ++r) {
+            const float v = S[(size_t)r * Qo + q];
+            if (v > best) { best = v; arg = r; }             // strict: first maximum wins (np.argmax)
+            any |= GT[(size_t)r * Qo + q] != 0;
+        }
+        s_best[q] = best;
+        s_hit[q] = GT[(size_t)arg * Qo + q] != 0;
+        my_gtp += any;
+        vmax = fmaxf(vmax, best); vmin = fminf(vmin, best);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+        vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+        my_gtp += __shfl_xor_sync(0xffffffffu, my_gtp, o);
+    }
+    if ((threadIdx.x & 31) == 0) { s_max[threadIdx.x >> 5] = vmax; s_min[threadIdx.x >> 5] = vmin; atomicAdd(&s_gtp, my_gtp); }
+    __syncthreads();
+    for (int i = 0; i < 8; ++i) { vmax = fmaxf(vmax, s_max[i]); vmin = fminf(vmin, s_min[i]); }
+    // np.linspace(start, stop, n): y_i = i * step + start in float64, last element = stop
+    const double start = (double)vmax, stop = (double)vmin;
+    const double step = __ddiv_rn(__dsub_rn(stop, start), (double)(n_thresh - 1));
+    for (int i = threadIdx.x; i < n_thresh; i += blockDim.x) {
+        // numpy: y = arange(n) * step; y += start  (two separately rounded float64 operations, no FMA)
+        const double t = (i == n_thresh - 1) ? stop : __dadd_rn(__dmul_rn((double)i, step), start);
+        unsigned long long a = 0, b = 0;
+        for (int q = 0; q < Qo; ++q) {
+            if ((double)s_best[q] >= t) { if (s_hit[q]) ++a; else ++b; }
+        }
+        tp[i] = a; fp[i] = b;
+    }
+    if (threadIdx.x == 0) gtp[0] = s_gtp;
+}
+
 }  // namespace lens
 
 using namespace lens;
+
+extern "C" int lens_pr_counts(const float *S, const uint8_t *GT, int Po, int Qo, int n_thresh, int64_t *tp,
+                              int64_t *fp, int64_t *gtp, void *stream)
+{
+    LENS_CHECK_ARG(S && GT && tp && fp && gtp, "lens_pr_counts: NULL buffer");
+    LENS_CHECK_ARG(Po > 0 && Qo > 0 && Qo <= 8192, "lens_pr_counts: need 0 < Qo <= 8192, Po > 0");
+    LENS_CHECK_ARG(n_thresh > 1, "lens_pr_counts: n_thresh must be > 1");
+    pr_counts_kernel<<<1, 256, (size_t)Qo * 5, as_stream(stream)>>>(
+        S, GT, Po, Qo, n_thresh, reinterpret_cast<unsigned long long *>(tp),
+        reinterpret_cast<unsigned long long *>(fp), reinterpret_cast<unsigned long long *>(gtp));
+    LENS_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" int lens_seqmatch_topk(const float *S, int B, int Q, int P, int L, int N, float *D_out,
                                   float *top_val, int32_t *top_idx, void *stream)

@@ -21,7 +21,7 @@ from .network import B200Network
 from .src import blitnet as bn
 from .src.dataset import CustomImageDataset, ProcessImage
 from .src.loggers import model_logger
-from .src.metrics import recallAtK  # noqa: F401  (re-exported like the reference module)
+from .src.metrics import recallAtK, createPR  # noqa: F401  (re-exported like the reference module)
 
 RECALL_NS = [1, 5, 10, 15, 20, 25]   # run_model.py:266
 
@@ -138,7 +138,10 @@ class LENS(nn.Module):
         self.GTtol = GTtol
 
         if getattr(self, "PR_curve", False):
-            raise LensError("--PR_curve (createPR, SURVEY 8f-1) is not part of lens_b200 yet")
+            if GTtol is None:
+                raise LensError("--PR_curve needs --matching (the reference fails the same way: GTtol undefined)")
+            LENS_P, LENS_R = createPR(dist_matrix_seq.T, GTtol.T, self.output_folder, matching="single", n_thresh=100)
+            self.lens_PR = {"Precision": LENS_P, "Recall": LENS_R}
         if getattr(self, "sad", False):
             raise LensError("--sad (sum-of-absolute-differences baseline) is not part of lens_b200 yet")
 

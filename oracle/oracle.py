@@ -268,3 +268,20 @@ def evaluate_tail(S, GT, L, tol, Ns=(1, 5, 10, 15, 20, 25), kind=None):
     GTtol = make_gt_tol(GT, L, tol)
     R = [round(recall_at_k(D, GTtol, K=n, kind=kind), 2) for n in Ns]
     return D, GTtol, R
+
+
+def create_pr(S_in, GThard, n_thresh=100):
+    """createPR(..., matching='single') of lens/src/metrics.py:21-139 without the figure -> (P, R) lists."""
+    S, GT = np.asarray(S_in), np.asarray(GThard).astype(bool)
+    gtp = np.count_nonzero(GT.any(0))
+    best_row = np.argmax(S, axis=0)
+    hit = GT[best_row, np.arange(GT.shape[1])]
+    best = np.max(S, axis=0)
+    P, R = [1], [0]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for t in np.linspace(best.max(), best.min(), n_thresh):
+            sel = best >= t
+            tp, fp = np.count_nonzero(hit & sel), np.count_nonzero(~hit & sel)
+            P.append(np.float64(tp) / np.float64(tp + fp))
+            R.append(np.float64(tp) / np.float64(gtp))
+    return P, R

@@ -160,6 +160,11 @@ def run_case(stub, name, argv, out_path, full_steps=2):
                               args.reference + "_" + args.query + "_GT.npy"))
     torch.manual_seed(50)
     U = torch.rand(T, args.roi_dim * args.roi_dim)
+    # precision-recall curve exactly as run_model.py:321 calls it (figure goes to the fake matplotlib)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        PR_P, PR_R = rm.createPR(rec["D"].T, rec["GTtol"].T, model.output_folder, matching="single", n_thresh=100)
     h = hashlib.sha256()
     for r in s2:
         h.update(r.to(torch.uint8).numpy().tobytes())
@@ -176,6 +181,7 @@ def run_case(stub, name, argv, out_path, full_steps=2):
         U_sha256=hashlib.sha256(U.numpy().tobytes()).hexdigest(),
         S=S.astype(np.uint16), D=rec["D"].astype(np.float32), GTtol=rec["GTtol"].astype(np.uint8),
         R=np.array(R, dtype=np.float64),
+        PR_P=np.array(PR_P, dtype=np.float64), PR_R=np.array(PR_R, dtype=np.float64),
         v0=iafs[0].v_mem.reshape(-1).numpy(), v1=iafs[1].v_mem.reshape(-1).numpy(),
         v2=iafs[2].v_mem.reshape(-1).numpy(),
         hidden_counts=hidden_counts.astype(np.uint16), in_counts=in_counts.astype(np.uint16),

@@ -123,3 +123,26 @@ def test_sequence_length_zero_branch(example_tree, monkeypatch):
     GTtol = O.make_gt_tol(g["GT"], 0, 3)
     want = [round(O.recall_at_k(S, GTtol, K=n, kind="stable"), 2) for n in (1, 5, 10, 15, 20, 25)]
     assert R == want
+
+
+def test_createPR_matches_reference(golden):
+    """CUDA createPR (matching='single') == the reference's own lists on both bundled runs."""
+    from lens_b200.src.metrics import createPR
+    for name in ("config1", "brisevent"):
+        g = golden(name)
+        P, R = createPR(g["D"].T, g["GTtol"].T, None, matching="single", n_thresh=100)
+        assert np.array_equal(np.array(P, dtype=np.float64), g["PR_P"], equal_nan=True)
+        assert np.array_equal(np.array(R, dtype=np.float64), g["PR_R"], equal_nan=True)
+
+
+def test_pr_curve_flag(example_tree, monkeypatch):
+    from lens_b200.config import default_args, generate_model_name
+    from lens_b200.run_model import LENS, run_inference
+    g, root = example_tree("config1", "example", "davis128", "example-reference", "example-query")
+    monkeypatch.chdir(root.parent)
+    args = default_args(matching=True, PR_curve=True, data_dir=str(root / "dataset") + "/")
+    args.quiet = True
+    model = LENS(args)
+    run_inference(model, generate_model_name(model), models_dir=str(root / "models"))
+    assert np.array_equal(np.array(model.lens_PR["Precision"], dtype=np.float64), g["PR_P"], equal_nan=True)
+    assert np.array_equal(np.array(model.lens_PR["Recall"], dtype=np.float64), g["PR_R"], equal_nan=True)

@@ -166,3 +166,12 @@ def test_forward_float_matches_raster_path(golden):
     sb = b.forward_float(x)
     assert np.array_equal(sb[0], outa[0].astype(np.float32))
     assert np.array_equal(sb[0].reshape(Q, T, -1).sum(1), ca[0])
+
+
+def test_create_pr_matches_reference(golden):
+    """createPR(matching='single') restatement == the reference's own function on both bundled runs."""
+    for name in ("config1", "brisevent"):
+        g = golden(name)
+        P, R = O.create_pr(g["D"].T, g["GTtol"].T)
+        assert np.array_equal(np.array(P, dtype=np.float64), g["PR_P"], equal_nan=True)
+        assert np.array_equal(np.array(R, dtype=np.float64), g["PR_R"], equal_nan=True)
