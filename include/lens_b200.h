@@ -163,6 +163,13 @@ int lens_recall(const int32_t *top_idx, int B, int Qo, int Po, int N, const uint
 int lens_pr_counts(const float *S, const uint8_t *GT, int Po, int Qo, int n_thresh, int64_t *tp,
                    int64_t *fp, int64_t *gtp, void *stream);
 
+/* Sum-of-absolute-differences baseline, lens/src/sad.py:25-42: dist[q][r] = sum_p |a[q][p] - b[r][p]|
+ * (torch.cdist(a, b, p=1) on float32 copies of uint8 frames; the sums are integers < 2^24, hence exact
+ * in fp32 in any order).  a [Q][npix] u8 (query frames), b [R][npix] u8 (reference frames),
+ * dist [Q][R] f32.  lens_reciprocal: out[i] = 1.0f / in[i] (IEEE, numpy's `1 / dist`).             */
+int lens_sad_matrix(const uint8_t *a, const uint8_t *b, int Q, int R, int npix, float *dist, void *stream);
+int lens_reciprocal(const float *in, int64_t n, float *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

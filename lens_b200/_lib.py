@@ -38,6 +38,8 @@ def _declare(L):
         "lens_snn_forward_range": (i32, [vp, vp, i32, i32, i32, vp, vp, vp, i32, vp]),
         "lens_snn_forward_float": (i32, [vp, vp, i32, i32, vp, vp]),
         "lens_seqmatch_topk": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]),
+        "lens_sad_matrix": (i32, [vp, vp, i32, i32, i32, vp, vp]),
+        "lens_reciprocal": (i32, [vp, i64, vp, vp]),
         "lens_pr_counts": (i32, [vp, vp, i32, i32, i32, vp, vp, vp, vp]),
         "lens_recall": (i32, [vp, i32, i32, i32, i32, vp, i64, vp, i32, pi32, i32, vp, vp, vp]),
     }

@@ -292,9 +292,59 @@ __global__ void __launch_bounds__(256) pr_counts_kernel(const float *__restrict_
     if (threadIdx.x == 0) gtp[0] = s_gtp;
 }
 
+// SAD baseline (lens/src/sad.py:38): one warp per (query, reference) pair, 16 pixels per lane-iteration
+// with byte-wise SIMD sum of absolute differences; integer accumulation (exact), stored as fp32.
+__global__ void __launch_bounds__(256) sad_kernel(const uint8_t *__restrict__ a, const uint8_t *__restrict__ b,
+                                                  int Q, int R, int npix, float *__restrict__ dist)
+{
+    const int lane = threadIdx.x & 31;
+    const long long pair = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    if (pair >= (long long)Q * R) return;
+    const int q = (int)(pair / R), r = (int)(pair - (long long)q * R);
+    const uint8_t *pa = a + (size_t)q * npix, *pb = b + (size_t)r * npix;
+    unsigned int acc = 0;
+    if ((npix & 15) == 0 && ((((uintptr_t)a | (uintptr_t)b)) & 15) == 0) {
+        const uint4 *va = reinterpret_cast<const uint4 *>(pa), *vb = reinterpret_cast<const uint4 *>(pb);
+        for (int i = lane; i < npix / 16; i += 32) {
+            const uint4 x = __ldg(va + i), y = __ldg(vb + i);
+            acc += __vsadu4(x.x, y.x) + __vsadu4(x.y, y.y) + __vsadu4(x.z, y.z) + __vsadu4(x.w, y.w);
+        }
+    } else {
+        for (int i = lane; i < npix; i += 32) acc += (unsigned)abs((int)pa[i] - (int)pb[i]);
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) dist[pair] = (float)acc;
+}
+
+__global__ void reciprocal_kernel(const float *__restrict__ in, int64_t n, float *__restrict__ out)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __fdiv_rn(1.0f, in[i]);
+}
+
 }  // namespace lens
 
 using namespace lens;
+
+extern "C" int lens_sad_matrix(const uint8_t *a, const uint8_t *b, int Q, int R, int npix, float *dist, void *stream)
+{
+    LENS_CHECK_ARG(a && b && dist, "lens_sad_matrix: NULL buffer");
+    LENS_CHECK_ARG(Q > 0 && R > 0 && npix > 0 && npix <= 65793, "lens_sad_matrix: need Q, R > 0 and 0 < npix <= 65793 "
+                   "(sums must stay below 2^24)");
+    const long long pairs = (long long)Q * R;
+    sad_kernel<<<(unsigned)((pairs * 32 + 255) / 256), 256, 0, as_stream(stream)>>>(a, b, Q, R, npix, dist);
+    LENS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int lens_reciprocal(const float *in, int64_t n, float *out, void *stream)
+{
+    LENS_CHECK_ARG(in && out && n >= 0, "lens_reciprocal: bad arguments");
+    if (n == 0) return 0;
+    reciprocal_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(in, n, out);
+    LENS_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" int lens_pr_counts(const float *S, const uint8_t *GT, int Po, int Qo, int n_thresh, int64_t *tp,
                               int64_t *fp, int64_t *gtp, void *stream)

@@ -103,3 +103,25 @@ def recall_counts(top_idx, Po, gt_dense=None, gt_center=None, gt_tol=0, ns=RECAL
                                  gt_tol, ns_arr, len(ns), ptr(hits), ptr(n_valid), stream_ptr()),
           "lens_recall")
     return hits, n_valid
+
+
+def sad_matrix(query_frames, reference_frames):
+    """u8 [Q, npix], u8 [R, npix] -> L1 distances f32 [Q, R] (torch.cdist(a, b, 1) of lens/src/sad.py:38)."""
+    require_cuda(query_frames, reference_frames)
+    assert query_frames.dtype == torch.uint8 and reference_frames.dtype == torch.uint8
+    Q, npix = query_frames.shape
+    R = reference_frames.shape[0]
+    assert reference_frames.shape[1] == npix
+    dist = torch.empty((Q, R), dtype=torch.float32, device=query_frames.device)
+    check(_lib.lib().lens_sad_matrix(ptr(query_frames), ptr(reference_frames), Q, R, npix, ptr(dist), stream_ptr()),
+          "lens_sad_matrix")
+    return dist
+
+
+def reciprocal(x):
+    """1 / x elementwise in IEEE fp32 (numpy's `1 / dist_matrix_seq`, lens/src/sad.py:52,62)."""
+    require_cuda(x)
+    assert x.dtype == torch.float32
+    out = torch.empty_like(x)
+    check(_lib.lib().lens_reciprocal(ptr(x), x.numel(), ptr(out), stream_ptr()), "lens_reciprocal")
+    return out

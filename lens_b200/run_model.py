@@ -143,7 +143,12 @@ class LENS(nn.Module):
             LENS_P, LENS_R = createPR(dist_matrix_seq.T, GTtol.T, self.output_folder, matching="single", n_thresh=100)
             self.lens_PR = {"Precision": LENS_P, "Recall": LENS_R}
         if getattr(self, "sad", False):
-            raise LensError("--sad (sum-of-absolute-differences baseline) is not part of lens_b200 yet")
+            if GTtol is None:
+                raise LensError("--sad needs --matching (the reference fails the same way: GTtol undefined)")
+            from .src.sad import run_sad
+            self.sad_PR, self.sad_Recall = run_sad(self.reference_dir, self.query_dir, GTtol, self.output_folder,
+                                                   self.sequence_length)
+            model.logger.info("SAD    " + "  ".join(f"{r:>5.2f}" for r in self.sad_Recall))
 
         model.logger.info("")
         model.logger.info("Succesfully completed inferencing using LENS")

@@ -80,8 +80,17 @@ def install_fakes():
             return f"{self.field_names} {getattr(self, 'row', None)}"
     _fake_module("prettytable", PrettyTable=PrettyTable)
     sk = _fake_module("skimage")
-    sk.io = _fake_module("skimage.io")
+
+    def imread(path):
+        from PIL import Image
+        return np.array(Image.open(path))
+    sk.io = _fake_module("skimage.io", imread=imread)
     return sinabs_stub
+
+
+def imread_u8(path):
+    from PIL import Image
+    return np.array(Image.open(path))
 
 
 def run_case(stub, name, argv, out_path, full_steps=2):
@@ -165,6 +174,23 @@ def run_case(stub, name, argv, out_path, full_steps=2):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         PR_P, PR_R = rm.createPR(rec["D"].T, rec["GTtol"].T, model.output_folder, matching="single", n_thresh=100)
+    # SAD baseline exactly as run_model.py:330 calls it (lens/src/sad.py, skimage.io.imread -> PIL)
+    import lens.src.sad as sad_mod
+    sad_rec = {}
+    real_cpr = sad_mod.createPR
+
+    def spy_createPR(S, GTm, *a, **k):
+        sad_rec["sim"] = np.array(S)
+        return real_cpr(S, GTm, *a, **k)
+    sad_mod.createPR = spy_createPR
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sad_PR, sad_Recall = sad_mod.run_sad(model.reference_dir, model.query_dir, rec["GTtol"], model.output_folder,
+                                             args.sequence_length)
+    ref_files = sorted(os.listdir(model.reference_dir), key=sad_mod.natural_sort_key)
+    ref_frames = np.stack([imread_u8(os.path.join(model.reference_dir, f)) for f in ref_files if f.endswith(".png")])
+    qry_files = sorted(os.listdir(model.query_dir), key=sad_mod.natural_sort_key)
+    sad_query_frames_equal = len([f for f in qry_files if f.endswith(".png")])
     h = hashlib.sha256()
     for r in s2:
         h.update(r.to(torch.uint8).numpy().tobytes())
@@ -182,6 +208,9 @@ def run_case(stub, name, argv, out_path, full_steps=2):
         S=S.astype(np.uint16), D=rec["D"].astype(np.float32), GTtol=rec["GTtol"].astype(np.uint8),
         R=np.array(R, dtype=np.float64),
         PR_P=np.array(PR_P, dtype=np.float64), PR_R=np.array(PR_R, dtype=np.float64),
+        ref_frames=ref_frames.astype(np.uint8), n_query_files=sad_query_frames_equal,
+        sad_sim=sad_rec["sim"].astype(np.float32), sad_recall=np.array(sad_Recall, dtype=np.float64),
+        sad_P=np.array(sad_PR["Precision"], dtype=np.float64), sad_R=np.array(sad_PR["Recall"], dtype=np.float64),
         v0=iafs[0].v_mem.reshape(-1).numpy(), v1=iafs[1].v_mem.reshape(-1).numpy(),
         v2=iafs[2].v_mem.reshape(-1).numpy(),
         hidden_counts=hidden_counts.astype(np.uint16), in_counts=in_counts.astype(np.uint16),

@@ -146,3 +146,44 @@ def test_pr_curve_flag(example_tree, monkeypatch):
     run_inference(model, generate_model_name(model), models_dir=str(root / "models"))
     assert np.array_equal(np.array(model.lens_PR["Precision"], dtype=np.float64), g["PR_P"], equal_nan=True)
     assert np.array_equal(np.array(model.lens_PR["Recall"], dtype=np.float64), g["PR_R"], equal_nan=True)
+
+
+def test_sad_baseline_matches_reference(golden):
+    """SAD baseline (lens/src/sad.py) on the GPU: 1/distance matrix, PR lists and Recall@N equal to the
+    reference's own run_sad outputs on both bundled datasets."""
+    from lens_b200 import ops
+    from lens_b200.src.sad import sad_distance_matrix
+    from lens_b200.src.metrics import createPR, recallAtK
+    for name in ("config1", "brisevent"):
+        g = golden(name)
+        L = int(g["sequence_length"])
+        q = torch.from_numpy(g["frames"].reshape(g["frames"].shape[0], -1))
+        r = torch.from_numpy(g["ref_frames"].reshape(g["ref_frames"].shape[0], -1))
+        D = sad_distance_matrix(q, r, L)
+        sim = ops.reciprocal(D.contiguous()).cpu().numpy()
+        assert np.array_equal(sim, g["sad_sim"])
+        P, R = createPR(sim, g["GTtol"], None, datatype="SAD", matching="single", n_thresh=100)
+        assert np.array_equal(np.array(P, dtype=np.float64), g["sad_P"], equal_nan=True)
+        assert np.array_equal(np.array(R, dtype=np.float64), g["sad_R"], equal_nan=True)
+        rec = [round(recallAtK(sim, g["GTtol"], K=n), 2) for n in (1, 5, 10, 15, 20, 25)]
+        for mine, ref, n in zip(rec, g["sad_recall"], (1, 5, 10, 15, 20, 25)):
+            lo, hi = O.recall_bounds(sim, g["GTtol"], n)
+            assert round(lo, 2) - 1e-9 <= mine <= round(hi, 2) + 1e-9
+            assert round(lo, 2) - 1e-9 <= ref <= round(hi, 2) + 1e-9
+
+
+def test_sad_flag(example_tree, monkeypatch, golden):
+    from lens_b200.config import default_args, generate_model_name
+    from lens_b200.run_model import LENS, run_inference
+    g, root = example_tree("config1", "example", "davis128", "example-reference", "example-query")
+    # the reference frames live next to the query frames in the reference's layout
+    rdir = root / "dataset" / "example" / "davis128" / "example-reference"
+    for i, fr in enumerate(g["ref_frames"]):
+        write_png_u8(str(rdir / f"image_{i:04d}.png"), fr)
+    monkeypatch.chdir(root.parent)
+    args = default_args(matching=True, PR_curve=True, sad=True, data_dir=str(root / "dataset") + "/")
+    args.quiet = True
+    model = LENS(args)
+    run_inference(model, generate_model_name(model), models_dir=str(root / "models"))
+    assert np.array_equal(np.array(model.sad_PR["Precision"], dtype=np.float64), g["sad_P"], equal_nan=True)
+    assert len(model.sad_Recall) == 6
