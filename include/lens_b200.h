@@ -170,6 +170,43 @@ int lens_pr_counts(const float *S, const uint8_t *GT, int Po, int Qo, int n_thre
 int lens_sad_matrix(const uint8_t *a, const uint8_t *b, int Q, int R, int npix, float *dist, void *stream);
 int lens_reciprocal(const float *in, int64_t n, float *out, void *stream);
 
+/* Online matcher of the event-driven deployment, lens/run_speck.py:155-226.
+ *
+ * lens_online_accumulate: one readout (run_speck.py:159-164, 188-198): sum[i] += (int32)counts[i]; when
+ * row_out != NULL also row_out[i] = floor(sum[i] / div) (`vector // 4`, the averaged sequence row).
+ *   sum [P] i32 device (running spike counts, NOT cleared between rows - the reference clears it only
+ *   after a match), counts [P] f32 device (integer-valued spike counts of one readout interval).
+ * lens_online_match: run_speck.py:200-204: result = scipy.signal.convolve2d(seq.T, eye(L), mode='same') / L
+ * and its per-column first-maximum argmax:
+ *   result[p][r] = (1/L) * sum_{a<L} seq[r + o - a][p + o - a],  o = (L-1)/2, zero outside the matrix.
+ *   seq [R][P] i32 device (sequence rows, oldest first), result [P][R] f64 device (integer sums, one
+ *   IEEE float64 division), argmax [R] i32 device.  1 <= L, R <= 64.                                */
+int lens_online_accumulate(int32_t *sum, const float *counts, int P, int div, int32_t *row_out, void *stream);
+int lens_online_match(const int32_t *seq, int R, int P, int L, double *result, int32_t *argmax, void *stream);
+
+/* Event-driven frame representation, lens/tools/dvstools.py:279-349 (tool='simple_rep').
+ *
+ * lens_event_windows: index ranges of the frames.  A frame that starts at time c holds the events with
+ * |t - c| <= interval (float64, the reference's own expression); the first later event that is not a hot
+ * pixel closes it, is dropped, and its timestamp is the next frame's c.  Frame 0 starts at `start`
+ * (events with t < start are skipped), or at t[0] when use_first_event != 0 (the reference's offset == 0
+ * case).  The frame still open at the end of the stream is not reported (the reference never saves it).
+ *   t [n] f64 device, seconds, ascending; x, y [n] u16 device
+ *   lut [sensor_h][sensor_w] i16 device: -2 hot pixel (event ignored entirely), -1 no slot, >= 0 slot
+ *   win_begin, win_end [max_windows] i64 device, win_t0 [max_windows] f64 device, n_windows [1] i64 device
+ *   unsorted: nullable [1] i32 device, set to 1 when t is not ascending (the ranges are then meaningless)
+ * lens_bin_events_lut: frames[w][slot] = (weight * #{events of range w whose pixel maps to slot}) mod 256
+ * (`frame_data[index] += accum_factor` on a uint8 vector, dvstools.py:310-322).
+ *   counts [n_windows][n_slots] u32 device scratch, frames [n_windows][n_slots] u8 device;
+ *   events_per_window_hint only sizes the grid.  x / y 16-byte aligned, n_slots <= 8192.              */
+int lens_event_windows(const double *t, const uint16_t *x, const uint16_t *y, int64_t n_events, const int16_t *lut,
+                       int sensor_w, int sensor_h, int use_first_event, double start, double interval,
+                       int64_t max_windows, int64_t *win_begin, int64_t *win_end, double *win_t0,
+                       int64_t *n_windows, int *unsorted, void *stream);
+int lens_bin_events_lut(const uint16_t *x, const uint16_t *y, const int16_t *lut, int sensor_w, int sensor_h,
+                        const int64_t *win_begin, const int64_t *win_end, int64_t n_windows, int n_slots, int weight,
+                        int64_t events_per_window_hint, uint32_t *counts, uint8_t *frames, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,6 +18,7 @@ class LensError(RuntimeError):
 def _declare(L):
     vp, i32, i64, u32, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_uint32, C.c_float
     pi32, pi64 = C.POINTER(C.c_int), C.POINTER(C.c_int64)
+    f64 = C.c_double
     sig = {
         "lens_version": (i32, [pi32, pi32]),
         "lens_last_error": (C.c_char_p, []),
@@ -40,6 +41,10 @@ def _declare(L):
         "lens_seqmatch_topk": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]),
         "lens_sad_matrix": (i32, [vp, vp, i32, i32, i32, vp, vp]),
         "lens_reciprocal": (i32, [vp, i64, vp, vp]),
+        "lens_online_accumulate": (i32, [vp, vp, i32, i32, vp, vp]),
+        "lens_online_match": (i32, [vp, i32, i32, i32, vp, vp, vp]),
+        "lens_event_windows": (i32, [vp, vp, vp, i64, vp, i32, i32, i32, f64, f64, i64, vp, vp, vp, vp, vp, vp]),
+        "lens_bin_events_lut": (i32, [vp, vp, vp, i32, i32, vp, vp, i64, i32, i32, i64, vp, vp, vp]),
         "lens_pr_counts": (i32, [vp, vp, i32, i32, i32, vp, vp, vp, vp]),
         "lens_recall": (i32, [vp, i32, i32, i32, i32, vp, i64, vp, i32, pi32, i32, vp, vp, vp]),
     }

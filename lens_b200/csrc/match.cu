@@ -322,9 +322,80 @@ __global__ void reciprocal_kernel(const float *__restrict__ in, int64_t n, float
     if (i < n) out[i] = __fdiv_rn(1.0f, in[i]);
 }
 
+// Online matcher (run_speck.py:155-226): a readout adds its spike counts to the running sums; every
+// `div` readouts the sums, floor-divided, become one sequence row.
+__global__ void online_accumulate_kernel(int32_t *__restrict__ sum, const float *__restrict__ counts, int P, int div,
+                                         int32_t *__restrict__ row_out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const int32_t s = sum[i] + (int32_t)counts[i];
+    sum[i] = s;
+    if (row_out) {
+        int32_t q = s / div;
+        if ((s % div != 0) && ((s < 0) != (div < 0))) --q;      // floor division like numpy's //
+        row_out[i] = q;
+    }
+}
+
+// result[p][r] = (1/L) sum_a seq[r+o-a][p+o-a] ('same' crop of the full convolution with eye(L)), then the
+// first maximum of every column r.  One CTA per column: coalesced reads along p for each of the L taps.
+__global__ void __launch_bounds__(256) online_match_kernel(const int32_t *__restrict__ seq, int R, int P, int L,
+                                                           double *__restrict__ result, int32_t *__restrict__ argmax)
+{
+    const int r = blockIdx.x, o = (L - 1) / 2;
+    double best = 0.0;
+    int best_p = 0x7fffffff;
+    bool have = false;
+    for (int p = threadIdx.x; p < P; p += blockDim.x) {
+        long long acc = 0;
+        for (int a = 0; a < L; ++a) {
+            const int rr = r + o - a, pp = p + o - a;
+            if (rr >= 0 && rr < R && pp >= 0 && pp < P) acc += seq[(size_t)rr * P + pp];
+        }
+        const double v = __ddiv_rn((double)acc, (double)L);
+        result[(size_t)p * R + r] = v;
+        if (!have || v > best) { best = v; best_p = p; have = true; }   // p ascending per thread: first max kept
+    }
+    __shared__ double sv[256];
+    __shared__ int sp[256];
+    sv[threadIdx.x] = best; sp[threadIdx.x] = best_p;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            const double v2 = sv[threadIdx.x + s];
+            const int p2 = sp[threadIdx.x + s];
+            const int p1 = sp[threadIdx.x];
+            if (p2 != 0x7fffffff && (p1 == 0x7fffffff || v2 > sv[threadIdx.x] || (v2 == sv[threadIdx.x] && p2 < p1))) {
+                sv[threadIdx.x] = v2; sp[threadIdx.x] = p2;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) argmax[r] = sp[0];
+}
+
 }  // namespace lens
 
 using namespace lens;
+
+extern "C" int lens_online_accumulate(int32_t *sum, const float *counts, int P, int div, int32_t *row_out, void *stream)
+{
+    LENS_CHECK_ARG(sum && counts, "lens_online_accumulate: NULL buffer");
+    LENS_CHECK_ARG(P > 0 && div != 0, "lens_online_accumulate: need P > 0 and div != 0");
+    online_accumulate_kernel<<<(unsigned)((P + 255) / 256), 256, 0, as_stream(stream)>>>(sum, counts, P, div, row_out);
+    LENS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int lens_online_match(const int32_t *seq, int R, int P, int L, double *result, int32_t *argmax, void *stream)
+{
+    LENS_CHECK_ARG(seq && result && argmax, "lens_online_match: NULL buffer");
+    LENS_CHECK_ARG(P > 0 && R >= 1 && R <= 64 && L >= 1 && L <= 64, "lens_online_match: need P > 0, 1 <= R, L <= 64");
+    online_match_kernel<<<(unsigned)R, 256, 0, as_stream(stream)>>>(seq, R, P, L, result, argmax);
+    LENS_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" int lens_sad_matrix(const uint8_t *a, const uint8_t *b, int Q, int R, int npix, float *dist, void *stream)
 {

@@ -125,3 +125,42 @@ def reciprocal(x):
     out = torch.empty_like(x)
     check(_lib.lib().lens_reciprocal(ptr(x), x.numel(), ptr(out), stream_ptr()), "lens_reciprocal")
     return out
+
+
+def event_windows(t, x, y, lut, use_first_event, start, interval, max_windows, check_sorted=True):
+    """Frame index ranges of the event-driven representation (lens/tools/dvstools.py:286-349).
+
+    t f64 [n] seconds ascending, x / y 16-bit [n], lut i16 [H, W] (-2 hot pixel, -1 unused, >= 0 slot).
+    -> (win_begin i64 [max_windows], win_end i64, win_t0 f64, n_windows i64 [1]); raises if t is unsorted."""
+    require_cuda(t, x, y, lut)
+    assert t.dtype == torch.float64 and x.dtype in (torch.int16, torch.uint16) and y.dtype == x.dtype
+    assert lut.dtype == torch.int16 and lut.dim() == 2
+    n = t.numel()
+    H, W = lut.shape
+    dev = t.device
+    nw = max(int(max_windows), 0)
+    wb = torch.empty(max(nw, 1), dtype=torch.int64, device=dev)
+    we = torch.empty(max(nw, 1), dtype=torch.int64, device=dev)
+    wt = torch.empty(max(nw, 1), dtype=torch.float64, device=dev)
+    n_win = torch.zeros(1, dtype=torch.int64, device=dev)
+    unsorted = torch.zeros(1, dtype=torch.int32, device=dev) if check_sorted else None
+    check(_lib.lib().lens_event_windows(ptr(t), ptr(x), ptr(y), n, ptr(lut), W, H, int(bool(use_first_event)),
+                                        float(start), float(interval), nw, ptr(wb), ptr(we), ptr(wt), ptr(n_win),
+                                        ptr(unsorted), stream_ptr()), "lens_event_windows")
+    if check_sorted and int(unsorted.item()):
+        raise ValueError("event timestamps must be ascending")
+    return wb, we, wt, n_win
+
+
+def bin_events_lut(x, y, lut, win_begin, win_end, n_slots, weight=1, events_per_window_hint=0):
+    """Slot histograms of the given event ranges -> frames u8 [n_windows, n_slots]
+    (`frame_data[index] += accum_factor`, dvstools.py:310-322; counts wrap mod 256)."""
+    require_cuda(x, y, lut, win_begin, win_end)
+    n_win = win_begin.numel()
+    H, W = lut.shape
+    frames = torch.empty((n_win, n_slots), dtype=torch.uint8, device=x.device)
+    counts = torch.empty((n_win, n_slots), dtype=torch.int32, device=x.device)
+    check(_lib.lib().lens_bin_events_lut(ptr(x), ptr(y), ptr(lut), W, H, ptr(win_begin), ptr(win_end), n_win, n_slots,
+                                         int(weight), int(events_per_window_hint), ptr(counts), ptr(frames),
+                                         stream_ptr()), "lens_bin_events_lut")
+    return frames

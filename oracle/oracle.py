@@ -285,3 +285,89 @@ def create_pr(S_in, GThard, n_thresh=100):
             P.append(np.float64(tp) / np.float64(tp + fp))
             R.append(np.float64(tp) / np.float64(gtp))
     return P, R
+
+
+def online_match(sequence, L):
+    """run_speck.py:200-204 restated with plain loops: convolve2d(sequence.T, eye(L), mode='same') / L
+    and the first-maximum argmax of every column.  sequence: int [R, P] (rows oldest first).
+    'same' keeps the [P, R] window of the full convolution that starts at offset (L-1)//2 in both axes."""
+    seq = np.asarray(sequence, dtype=np.int64)
+    R, P = seq.shape
+    o = (L - 1) // 2
+    result = np.zeros((P, R), dtype=np.float64)
+    for p in range(P):
+        for r in range(R):
+            acc = 0
+            for a in range(L):
+                rr, pp = r + o - a, p + o - a
+                if 0 <= rr < R and 0 <= pp < P:
+                    acc += int(seq[rr, pp])
+            result[p, r] = np.float64(acc) / np.float64(L)
+    return result, np.argmax(result, axis=0)
+
+
+class OnlineMatcherOracle:
+    """State machine of run_speck.py:155-226 (custom_readout + seq_match), one push() per readout."""
+
+    def __init__(self, reference_places, sequence_length, readouts_per_row=4, rows_per_match=4):
+        self.P, self.L = reference_places, sequence_length
+        self.per_row, self.per_match = readouts_per_row, rows_per_match
+        self.sum = np.zeros(self.P, dtype=np.int64)     # run_speck.py:159-164 (dict feature -> count)
+        self.qry = 0
+        self.sequence = None
+        self.matrix = None
+
+    def push(self, counts):
+        self.sum += np.asarray(counts).astype(np.int64)
+        self.qry += 1                                   # :169
+        if self.qry != self.per_row:                    # :180
+            return None
+        self.qry = 0                                    # :226
+        row = self.sum // self.per_row                  # :195,198 (sum keeps accumulating across rows)
+        self.sequence = row[None] if self.sequence is None else np.vstack((self.sequence, row))
+        if self.sequence.shape[0] != self.per_match:    # :200
+            return None
+        result, arg = online_match(self.sequence, self.L)
+        self.matrix = result if self.matrix is None else np.concatenate((self.matrix, result), axis=1)   # :213-217
+        self.sum = np.zeros(self.P, dtype=np.int64)     # :221
+        self.sequence = None                            # :222
+        return arg, result
+
+
+def simple_rep(t, x, y, dimensions, unique_indices, centroid_dict, hot_pixels, timebin_fps, offset=0.0,
+               accum_factor=1.0, frames_max=900, frame_limit=False):
+    """FrameRep.event_data, text branch with tool='simple_rep' (lens/tools/dvstools.py:173-349), restated
+    event by event.  dimensions = (height, width); centroid_dict {flat pixel: flat centroid};
+    -> (frames u8 [n, pixels] in the order the reference saves them, offset the reference ends up with)."""
+    H, W = dimensions
+    pixels = len(unique_indices)
+    frame_interval = 1.0 / timebin_fps                               # :174
+    start = current = None
+    if offset != 0:                                                  # :175-177
+        start = current = offset
+    frame = np.zeros(pixels, dtype=np.uint8)
+    saved = {}
+    frame_number = 0
+    uniq = np.asarray(unique_indices)
+    for ts, xe, ye in zip(t, x, y):
+        ts, xe, ye = float(ts), int(xe), int(ye)
+        if offset == 0:                                              # :286-290
+            offset = ts
+            start = current = ts
+        if ts < start or (hot_pixels and (xe, ye) in hot_pixels):    # :293-294
+            continue
+        if abs(ts - current) <= frame_interval:                      # :297
+            flat = ye * W + xe
+            if flat in centroid_dict:                                # :310-323
+                slot = int(np.where(uniq == centroid_dict[flat])[0][0])
+                frame[slot] = np.uint8(int(float(frame[slot]) + accum_factor) & 255)
+        else:                                                        # :326-349
+            saved[frame_number] = frame.copy()                       # save_frame(frame_data, frame_number)
+            if not ts <= offset:
+                frame_number += 1
+            frame = np.zeros(pixels, dtype=np.uint8)
+            current = ts
+            if frame_number >= frames_max and frame_limit:
+                break
+    n = max(saved) + 1 if saved else 0
+    return np.stack([saved[i] for i in range(n)]) if n else np.zeros((0, pixels), np.uint8), offset

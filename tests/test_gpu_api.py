@@ -187,3 +187,26 @@ def test_sad_flag(example_tree, monkeypatch, golden):
     run_inference(model, generate_model_name(model), models_dir=str(root / "models"))
     assert np.array_equal(np.array(model.sad_PR["Precision"], dtype=np.float64), g["sad_P"], equal_nan=True)
     assert len(model.sad_Recall) == 6
+
+
+def test_online_matcher_matches_reference_arithmetic():
+    """OnlineMatcher (run_speck.py:155-226 on the GPU) against the oracle state machine and scipy."""
+    from scipy.signal import convolve2d
+    from lens_b200.online import OnlineMatcher
+    rng = np.random.default_rng(21)
+    for P, L in [(100, 4), (1000, 2), (37, 5), (8, 1)]:
+        gpu, cpu = OnlineMatcher(P, L), O.OnlineMatcherOracle(P, L)
+        n_match = 0
+        for i in range(40):
+            counts = rng.integers(0, 12, size=P).astype(np.float32)
+            a, b = gpu.push(torch.from_numpy(counts).cuda()), cpu.push(counts)
+            assert (a is None) == (b is None)
+            if a is not None:
+                n_match += 1
+                assert np.array_equal(a[0].cpu().numpy(), b[0])
+                assert np.array_equal(a[1].cpu().numpy(), b[1])
+                seq = gpu.sequence.cpu().numpy()
+                ref = convolve2d(seq.T, np.eye(L, dtype=np.float32), mode="same") / L
+                assert np.array_equal(a[1].cpu().numpy(), ref)
+        assert n_match == 2
+        assert np.array_equal(gpu.similarity_matrix().cpu().numpy(), cpu.matrix.T)

@@ -3,10 +3,14 @@
 Goldens: tests/golden/make_golden.py ran /root/reference's run_model.LENS.evaluate,
 dataset.CustomImageDataset and metrics.recallAtK (sinabs restated, see sinabs_stub.py).
 """
+import os
+
 import numpy as np
 import pytest
 
 from oracle import oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def _setup(g):
@@ -175,3 +179,114 @@ def test_create_pr_matches_reference(golden):
         P, R = O.create_pr(g["D"].T, g["GTtol"].T)
         assert np.array_equal(np.array(P, dtype=np.float64), g["PR_P"], equal_nan=True)
         assert np.array_equal(np.array(R, dtype=np.float64), g["PR_R"], equal_nan=True)
+
+
+def test_online_match_against_scipy():
+    """The online matcher's arithmetic is scipy.signal.convolve2d(mode='same') (run_speck.py:202): pin the
+    loop restatement against scipy itself, the library the reference calls."""
+    from scipy.signal import convolve2d
+    rng = np.random.default_rng(11)
+    for P, R, L in [(7, 4, 1), (25, 4, 2), (100, 4, 4), (33, 4, 5), (9, 6, 3), (5, 4, 7)]:
+        seq = rng.integers(0, 40, size=(R, P))
+        result, arg = O.online_match(seq, L)
+        ref = convolve2d(seq.T, np.eye(L, dtype=np.float32), mode="same") / L
+        assert ref.dtype == result.dtype and np.array_equal(ref, result)
+        assert np.array_equal(arg, np.argmax(ref, axis=0))
+
+
+def test_online_matcher_state_machine():
+    """4 readouts -> one row (cumulative sum // 4), 4 rows -> one match, then the sums restart."""
+    rng = np.random.default_rng(12)
+    P, L = 30, 3
+    m = O.OnlineMatcherOracle(P, L)
+    pushes = rng.integers(0, 9, size=(32, P)).astype(np.float32)
+    outs = [m.push(c) for c in pushes]
+    done = [i for i, o in enumerate(outs) if o is not None]
+    assert done == [15, 31]
+    cum = np.cumsum(pushes[:16].astype(np.int64), axis=0)
+    seq = np.stack([cum[3], cum[7], cum[11], cum[15]]) // 4
+    assert np.array_equal(outs[15][1], O.online_match(seq, L)[0])
+    assert m.matrix.shape == (P, 8)
+
+
+def _load_event_cases():
+    import json
+    g = np.load(os.path.join(GOLDEN, "events_simple_rep.npz"))
+    W, H = (int(v) for v in g["sensor"])
+    for name in ("plain", "hot_gaps", "offset", "limit"):
+        lines = [str(s) for s in g[name + "/lines"]]
+        t = np.array([float(l.split()[0]) for l in lines])       # float(): what the reference calls per field
+        x = np.array([int(float(l.split()[1])) for l in lines])
+        y = np.array([int(float(l.split()[2])) for l in lines])
+        args = dict(timebin=10.0, accum_factor=1.0, offset=0.0, frames_max=900, frame_limit=False, pixels=25)
+        args.update(json.loads(str(g[name + "/args"])))
+        hot = set((int(a), int(b)) for a, b in g[name + "/hot"]) or None
+        cdict = {int(k): int(v) for k, v in zip(g[name + "/dict_keys"], g[name + "/dict_vals"])}
+        yield name, g, (W, H), lines, t, x, y, args, hot, cdict
+
+
+def test_simple_rep_oracle_against_reference_frames():
+    """The event-by-event restatement reproduces every PNG the reference's FrameRep wrote (reference and
+    query mode write the same frames from the same layout)."""
+    n_frames = 0
+    for name, g, (W, H), lines, t, x, y, args, hot, cdict in _load_event_cases():
+        uniq = g[name + "/unique_indices"]
+        frames, offset = O.simple_rep(t, x, y, (H, W), uniq, cdict, hot, args["timebin"], args["offset"],
+                                      args["accum_factor"], args["frames_max"], args["frame_limit"])
+        side = int(np.sqrt(args["pixels"]))
+        want = g[name + "/frames_ref"]
+        assert np.array_equal(want, g[name + "/frames_qry"])
+        assert frames.reshape(-1, side, side).shape == want.shape, name
+        assert np.array_equal(frames.reshape(-1, side, side), want), name
+        assert offset == float(g[name + "/offset_after"])
+        assert want.any()
+        n_frames += len(want)
+    assert n_frames > 50
+
+
+def test_event_text_reader_parses_like_float():
+    """Host reader (pandas C parser, round-trip precision) == the reference's float()/int() per field."""
+    import tempfile
+    from lens_b200.tools import dvstools
+    for name, g, (W, H), lines, t, x, y, args, hot, cdict in _load_event_cases():
+        with tempfile.TemporaryDirectory() as d:
+            import zipfile
+            zp = os.path.join(d, "syn.zip")
+            with zipfile.ZipFile(zp, "w") as z:
+                z.writestr("syn.txt", "{} {}\n".format(W, H) + "\n".join(lines) + "\n")
+                z.writestr("event_sum.txt", str(len(lines)))
+            ev = dvstools.read_events_zip(zp)
+            assert (ev["width"], ev["height"], ev["event_sum"]) == (W, H, len(lines))
+            assert np.array_equal(ev["t"], t) and np.array_equal(ev["x"], x) and np.array_equal(ev["y"], y)
+            # writer round trip (ExtractRosbag's '{:.12f}' format)
+            zp2 = os.path.join(d, "again.zip")
+            dvstools.write_events_zip(zp2, ev["t"], ev["x"], ev["y"], ev["p"], W, H)
+            ev2 = dvstools.read_events_zip(zp2)
+            assert np.array_equal(ev2["t"], t) and np.array_equal(ev2["p"], ev["p"])
+        break
+
+
+def test_patch_layout_matches_reference_layout():
+    """make_patch_layout draws the same centroids / patch ownership as dvstools.py:221-244 for the same
+    numpy global seed (the golden run used np.random.seed(7))."""
+    from lens_b200.tools import dvstools
+    for name, g, (W, H), lines, t, x, y, args, hot, cdict in _load_event_cases():
+        np.random.seed(7)
+        uniq, d = dvstools.make_patch_layout((H, W), args["pixels"])
+        assert np.array_equal(uniq, g[name + "/unique_indices"])
+        assert d == cdict and list(d.keys()) == list(cdict.keys())
+        lut = dvstools.layout_lut((H, W), uniq, d, hot)
+        assert lut.shape == (H, W) and (lut >= 0).sum() == len(set(d) - {hy * W + hx for hx, hy in (hot or ())})
+
+
+def test_dataset_csv_matches_reference_writer(tmp_path):
+    """create_csv_from_images writes the bytes the reference's writer wrote for the same folder listing."""
+    from lens_b200.tools.create_data_csv import create_csv_from_images, haversine
+    g = np.load(os.path.join(GOLDEN, "events_simple_rep.npz"))
+    for f in g["plain/files_ref"]:
+        (tmp_path / str(f)).write_bytes(b"")
+    (tmp_path / "notes.txt").write_text("ignored")
+    out = tmp_path / "out.csv"
+    create_csv_from_images(str(tmp_path), str(out))
+    assert open(out).read() == str(g["plain/csv"])        # the golden was read in text mode too
+    assert abs(haversine(153.0, -27.5, 153.0, -27.5)) == 0 and 110e3 < haversine(153.0, -27.0, 153.0, -28.0) < 112e3
