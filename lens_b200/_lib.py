@@ -62,9 +62,11 @@ def lib():
     """Load lens_b200/liblens_b200.so (building it with nvcc if the sources are newer)."""
     global _lib, EXPORTS
     if _lib is None:
-        path = _build.SO_PATH
-        if _build.needs_build():
-            path = _build.build()
+        path = os.environ.get("LENS_B200_LIB")      # e.g. an instrumented build from tools/ (profiling only)
+        if not path:
+            path = _build.SO_PATH
+            if _build.needs_build():
+                path = _build.build()
         if not os.path.exists(path):
             raise LensError(f"{path} is missing: run `python -m lens_b200.build`")
         L = C.CDLL(path)

@@ -34,6 +34,8 @@
 #include "snn.cuh"
 
 #include <algorithm>
+#include <cstdio>
+#include <vector>
 
 namespace lens {
 
@@ -200,7 +202,22 @@ struct Params {
     int8_t *S1_out;         // [pairs][chunks][out_Fp/16][64][16]
     int out_Fp;
     int64_t *overflow;      // spike counts above LENS_MAX_SPIKE
+#ifdef LENS_TC_PROFILE
+    long long *prof;        // [gridDim.x][16] phase clocks of warps 1, 4 and 8 (profiling builds only)
+#endif
 };
+
+#ifdef LENS_TC_PROFILE
+#define PROF_DECL long long prof_t = clock64(), prof_acc[6] = {0, 0, 0, 0, 0, 0}
+#define PROF(i) do { const long long now_ = clock64(); prof_acc[i] += now_ - prof_t; prof_t = now_; } while (0)
+#define GANTT(k) do { if (blockIdx.x == 0 && lane == 0 && (int)it >= 1000 && (int)it < 1003) p.prof[1024 * 24 + ((int)it - 1000) * 48 + (k)] = clock64(); } while (0)
+#define PROF_FLUSH(base) do { if (lane == 0) for (int i_ = 0; i_ < 6; ++i_) p.prof[blockIdx.x * 24 + (base) + i_] = prof_acc[i_]; } while (0)
+#else
+#define PROF_DECL
+#define PROF(i)
+#define GANTT(k)
+#define PROF_FLUSH(base)
+#endif
 
 __device__ __forceinline__ void bulk_s2g(void *gmem_dst, const void *smem_src, uint32_t bytes)
 {
@@ -313,56 +330,67 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
                 __syncwarp();
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer (warp-uniform, one elected lane issues) ================
+    } else {
+        // ===================== MMA issuers: warp 1 + g owns plane pair g (one elected lane issues) =========
+        // Three issuing warps instead of one: the commit of a pair and the wait for its accumulators to be
+        // drained cost the issuing warp ~450 cycles per pair, during which a single issuer cannot feed the
+        // tensor pipe; with one warp per pair those latencies overlap the other pairs' MMAs.
+        const int g = warp - 1;
         const uint32_t idesc = make_idesc(kM, kN);
         // descriptors differ only in the 14-bit start-address field: precompute, then add offsets
         const uint64_t da0 = make_desc(smem_u32(sA), kM * 16, 128);
         const uint64_t db0 = make_desc(smem_u32(sB), kN * 16, 128);
         const uint32_t a_plane = plane_bytes >> 4, a_kstep = (2 * kM * 16) >> 4;
         const uint32_t b_stage = tile_bytes >> 4, b_kstep = (2 * kN * 16) >> 4;
+        // the two planes of the pair are interleaved along K so that consecutive MMAs accumulate into
+        // different TMEM tiles (no back-to-back accumulator dependency)
+        const uint64_t da_a = da0 + (uint32_t)(2 * g) * a_plane, da_b = da_a + a_plane;
+        const uint32_t d_a = tmem_base + (2 * g) * kN, d_b = d_a + kN;
         uint32_t it = 0, a_phase = 0;
         int cur_tile = -1;
+        PROF_DECL;
         for (int item = item0; item < item1; ++item) {
             const int tile = item / p.n_pairs;
             if (tile != cur_tile) { mbar_wait(a_full, a_phase); a_phase ^= 1; cur_tile = tile; }   // planes landed
+            PROF(0);
             for (int c = 0; c < p.chunks; ++c, ++it) {
                 const uint32_t stage = it % kStages, phase = (it / kStages) & 1;
+                GANTT(0 + 5 * g);
                 mbar_wait(b_full + stage, phase);           // spikes landed
+                PROF(1);
+                GANTT(1 + 5 * g);
                 const uint64_t db_s = db0 + stage * b_stage;
-                // The accumulator set is handed over in plane pairs: the MMAs of pair g of this tile
-                // start as soon as the epilogue has drained pair g of the previous tile, and the
-                // epilogue starts draining pair g while pairs g+1.. are still being computed.
-#pragma unroll 1
-                for (int g = 0; g < 3; ++g) {
-                    mbar_wait(acc_empty + g, (it & 1) ^ 1);
-                    tc_fence_after();
-                    if (elect_one()) {
-                        // the two planes of the pair are interleaved along K so that consecutive MMAs
-                        // accumulate into different TMEM tiles (no back-to-back accumulator dependency)
-                        const uint64_t da_a = da0 + (uint32_t)(2 * g) * a_plane, da_b = da_a + a_plane;
-                        const uint32_t d_a = tmem_base + (2 * g) * kN, d_b = d_a + kN;
-                        if (kKSteps > 0) {
+                // The accumulator set is handed over in plane pairs: the MMAs of pair g of this tile start
+                // as soon as the epilogue has drained pair g of the previous tile, and the epilogue starts
+                // draining pair g while the other pairs are still being computed.
+                mbar_wait(acc_empty + g, (it & 1) ^ 1);
+                tc_fence_after();
+                PROF(2);
+                GANTT(2 + 5 * g);
+                if (elect_one()) {
+                    if (kKSteps > 0) {
 #pragma unroll
-                            for (int ks = 0; ks < kKSteps; ++ks) {
-                                mma_i8(d_a, da_a + ks * a_kstep, db_s + ks * b_kstep, idesc, ks > 0 ? 1u : 0u);
-                                mma_i8(d_b, da_b + ks * a_kstep, db_s + ks * b_kstep, idesc, ks > 0 ? 1u : 0u);
-                            }
-                        } else {
-                            for (int ks = 0; ks < ksteps; ++ks) {
-                                mma_i8(d_a, da_a + ks * a_kstep, db_s + ks * b_kstep, idesc, ks > 0 ? 1u : 0u);
-                                mma_i8(d_b, da_b + ks * a_kstep, db_s + ks * b_kstep, idesc, ks > 0 ? 1u : 0u);
-                            }
+                        for (int ks = 0; ks < kKSteps; ++ks) {
+                            mma_i8(d_a, da_a + ks * a_kstep, db_s + ks * b_kstep, idesc, ks > 0 ? 1u : 0u);
+                            mma_i8(d_b, da_b + ks * a_kstep, db_s + ks * b_kstep, idesc, ks > 0 ? 1u : 0u);
                         }
-                        tc_commit(acc_full + g);               // this pair is ready for the drain warps
-                        // (every commit costs the tensor pipe ~150 cycles, so the shared-memory slot is
-                        //  released by the drain warpgroup when it sees the last pair complete)
+                    } else {
+                        for (int ks = 0; ks < ksteps; ++ks) {
+                            mma_i8(d_a, da_a + ks * a_kstep, db_s + ks * b_kstep, idesc, ks > 0 ? 1u : 0u);
+                            mma_i8(d_b, da_b + ks * a_kstep, db_s + ks * b_kstep, idesc, ks > 0 ? 1u : 0u);
+                        }
                     }
-                    __syncwarp();
+                    GANTT(3 + 5 * g);
+                    tc_commit(acc_full + g);               // this pair is ready for the drain warps
+                    // (the shared-memory slot of the spike tile is released by the drain warpgroup when it
+                    //  has seen all three pairs complete)
                 }
                 __syncwarp();
+                PROF(3);
+                GANTT(4 + 5 * g);
             }
         }
+        if (warp == 1) PROF_FLUSH(0);
     }
     } else if (warp < 8) {
         // ===================== drain warpgroup: TMEM accumulators -> exact fp32 contraction results ==========
@@ -370,6 +398,7 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
         const int quarter = warp & 3;                          // TMEM lanes this warp may touch
         const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
         int it = 0;
+        PROF_DECL;
         for (int item = item0; item < item1; ++item) {
         const int place = (item / p.n_pairs) * kM + quarter * 32 + lane;
         const float scale = place < p.P ? p.scale[place] : 0.0f;
@@ -378,8 +407,12 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
             int32_t xl[kN], xh[kN];
 #pragma unroll
             for (int g = 0; g < 3; ++g) {
+                PROF(1);
+                if (g == 0) GANTT(16);
                 mbar_wait(acc_full + g, it & 1);
                 tc_fence_after();
+                PROF(0);
+                GANTT(17 + 2 * g);
 #pragma unroll
                 for (int h = 0; h < kN / 16; ++h) {
                     int32_t lo[16], hi[16];
@@ -403,6 +436,7 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
                 }
                 tc_fence_before();
                 __syncwarp();
+                GANTT(18 + 2 * g);
                 if (lane == 0) {
                     mbar_arrive(acc_empty + g);                  // pair g is free for the next tile's MMAs
                     // all MMAs of this tile have retired: its spike tile may be overwritten by the TMA
@@ -411,8 +445,11 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
             }
             // one rounding to fp32 (cvt.rn.f32.s64), exact power-of-two scale, hand over through TMEM
             const uint32_t xb = it & 1;
+            PROF(1);
             mbar_wait(x_empty + xb, ((it >> 1) & 1) ^ 1);
             tc_fence_after();
+            PROF(2);
+            GANTT(23);
 #pragma unroll
             for (int h = 0; h < kN / 16; ++h) {
                 float xf[16];
@@ -427,8 +464,11 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(x_full + xb);
+            PROF(3);
+            GANTT(24);
         }
         }
+        if (warp == 4) PROF_FLUSH(6);
     } else {
         // ===================== scan warpgroup: IAF#2 recurrence of both streams, spike counts ================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsScan));
@@ -438,6 +478,7 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
         const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
         long long n_over = 0;
         int it = 0;
+        PROF_DECL;
         for (int item = item0; item < item1; ++item) {
             const int tile = item / p.n_pairs, pr = item - tile * p.n_pairs;
             const int place = tile * kM + quarter * 32 + lane;
@@ -451,8 +492,12 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
             for (int c = 0; c < p.chunks; ++c, ++it) {
                 const uint32_t xb = it & 1;
                 float x[kN];
+                PROF(1);
+                GANTT(32);
                 mbar_wait(x_full + xb, (it >> 1) & 1);
                 tc_fence_after();
+                PROF(0);
+                GANTT(33);
 #pragma unroll
                 for (int h = 0; h < kN / 16; ++h) {
                     float t16[16];
@@ -464,6 +509,8 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(x_empty + xb);
+                PROF(2);
+                GANTT(34);
                 if (!kHidden && !live0 && !live1) continue;
                 // hidden layer: this tile's spike bytes are staged in shared memory [kc][row = stream*32+n][16]
                 uint8_t *stage_out = sOut + (it & 1) * 8192 + (quarter * 2 + (lane >> 4)) * 1024 + (lane & 15);
@@ -570,6 +617,8 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
                         }
                     }
                 }
+                PROF(3);
+                GANTT(35);
                 // advance the shared timeline by the tile's valid steps
                 t_in_q += nvalid;
                 while (t_in_q >= p.T) { t_in_q -= p.T; ++q; }
@@ -591,6 +640,7 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
             if (live0) p.v2[(size_t)b0 * p.P + place] = v0;
             if (live1) p.v2[(size_t)b1 * p.P + place] = v1;
         }
+        if (warp == 8) PROF_FLUSH(12);
         if (kHidden) {
             if (warp == 8 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
             if (n_over) atomicAdd((unsigned long long *)p.overflow, (unsigned long long)n_over);
@@ -742,6 +792,39 @@ int snn_tc_output(SnnHandle *h, const int8_t *S1, int nb, int b0, int steps, flo
     p.n_tiles = h->P_tiles;
     const size_t smem = tc::smem_bytes(h->Fp);
     dim3 grid((unsigned)std::min<long long>(sms, (long long)h->P_tiles * p.n_pairs));
+#ifdef LENS_TC_PROFILE
+    static long long *prof_dev = nullptr;
+    if (!prof_dev) cudaMalloc(&prof_dev, (1024 * 24 + 256) * sizeof(long long));
+    cudaMemsetAsync(prof_dev, 0, (1024 * 24 + 256) * sizeof(long long), st);
+    p.prof = prof_dev;
+    struct ProfDump {
+        long long *d; unsigned n; cudaStream_t st; long long iters;
+        ~ProfDump()
+        {
+            std::vector<long long> hbuf(n * 24);
+            cudaStreamSynchronize(st);
+            cudaMemcpy(hbuf.data(), d, hbuf.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+            double avg[18] = {0};
+            for (unsigned b = 0; b < n; ++b) for (int i = 0; i < 18; ++i) avg[i] += (double)hbuf[b * 24 + i] / n / iters;
+            fprintf(stderr, "[tc-prof] clk per tile-iteration (avg over %u CTAs, %lld iters/CTA)\n", n, iters);
+            fprintf(stderr, "  mma  : planes-wait %.0f  b_full-wait %.0f  acc_empty-wait %.0f  issue %.0f\n", avg[0], avg[1], avg[2], avg[3]);
+            fprintf(stderr, "  drain: acc_full-wait %.0f  fold %.0f  x_empty-wait %.0f  convert+st %.0f\n", avg[6], avg[7], avg[8], avg[9]);
+            long long g_[144];
+            cudaMemcpy(g_, d + 1024 * 24, sizeof(g_), cudaMemcpyDeviceToHost);
+            const long long t0_ = g_[0];
+            for (int r = 0; r < 3; ++r) {
+                fprintf(stderr, "  gantt it=%d  mma:", 1000 + r);
+                for (int k = 0; k <= 14; ++k) fprintf(stderr, " %lld", g_[r * 48 + k] - t0_);
+                fprintf(stderr, "  | drain:");
+                for (int k = 16; k <= 24; ++k) fprintf(stderr, " %lld", g_[r * 48 + k] - t0_);
+                fprintf(stderr, "  | scan:");
+                for (int k = 32; k <= 35; ++k) fprintf(stderr, " %lld", g_[r * 48 + k] - t0_);
+                fprintf(stderr, "\n");
+            }
+            fprintf(stderr, "  scan : x_full-wait %.0f  other %.0f  load %.0f  chain %.0f\n", avg[12], avg[13], avg[14], avg[15]);
+        }
+    } prof_dump{prof_dev, grid.x, st, (long long)h->P_tiles * p.n_pairs * p.chunks / grid.x};
+#endif
     LaunchTimer timer(h, st, 1);
     const bool unit = h->thr == 1.0f && h->vmin == -1.0f, dbg = out_steps != nullptr;
 #define LENS_TC_LAUNCH(U, D)                                     \
@@ -786,6 +869,11 @@ int snn_tc_hidden(SnnHandle *h, const uint8_t *pooled, int nb, int b0, int steps
     p.P = h->F; p.Fp = h->Ip; p.T = h->T; p.steps = steps; p.chunks = chunks; p.nb = nb; p.n_pairs = n_pairs;
     p.thr = h->thr; p.vmin = h->vmin;
     p.S1_out = h->S1; p.out_Fp = h->Fp; p.overflow = h->counters;
+#ifdef LENS_TC_PROFILE
+    static long long *prof_dev_h = nullptr;
+    if (!prof_dev_h) cudaMalloc(&prof_dev_h, (1024 * 24 + 256) * sizeof(long long));
+    p.prof = prof_dev_h;
+#endif
     const int sms = std::max(sm_count(), 1);
     p.n_tiles = h->F_tiles;
     const size_t smem = tc::smem_bytes(h->Ip, true);
