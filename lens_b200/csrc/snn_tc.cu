@@ -100,6 +100,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
     while (!mbar_try_wait(bar, parity)) {}
 }
+// Non-blocking probe.  A barrier poll takes ~150 cycles to return even when the phase is already
+// complete; issued early, its latency hides behind independent work and mbar_wait_probed() is free
+// in the common case.
+__device__ __forceinline__ uint32_t mbar_probe(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok;
+}
+__device__ __forceinline__ void mbar_wait_probed(uint32_t probed, uint64_t *bar, uint32_t parity)
+{
+    if (!probed) mbar_wait(bar, parity);
+}
 __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -398,58 +419,82 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
         const int quarter = warp & 3;                          // TMEM lanes this warp may touch
         const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
         int it = 0;
+        uint32_t probe0 = 0;
         PROF_DECL;
         for (int item = item0; item < item1; ++item) {
         const int place = (item / p.n_pairs) * kM + quarter * 32 + lane;
         const float scale = place < p.P ? p.scale[place] : 0.0f;
         for (int c = 0; c < p.chunks; ++c, ++it) {
-            // X = sum_j P_j 256^j as (xh:xl) for the 64 columns of this lane
+            // X = sum_j P_j 256^j as (xh:xl) for the 64 columns of this lane.  The 12 (pair, 16-column) loads
+            // are double-buffered in registers: the tcgen05.ld of step s + 1 is in flight while step s is
+            // folded into X, so only the first load's latency is exposed.
             int32_t xl[kN], xh[kN];
+            int32_t buf[2][32];
+            uint32_t probe = 0;
+            constexpr int kH = kN / 16, kSteps = 3 * kH;
+            PROF(1);
+            GANTT(16);
+            mbar_wait_probed(probe0, acc_full + 0, it & 1);
+            tc_fence_after();
+            // in steady state the MMA warps are a tile ahead: poll the other two pairs now, so that the
+            // polls' latency hides behind the first pair's loads and folding
+            const uint32_t probe1 = mbar_probe(acc_full + 1, it & 1), probe2 = mbar_probe(acc_full + 2, it & 1);
+            PROF(0);
+            GANTT(17);
+            tmem_ld16(tlane + 0 * kN, reinterpret_cast<int32_t(&)[16]>(buf[0][0]));
+            tmem_ld16(tlane + 1 * kN, reinterpret_cast<int32_t(&)[16]>(buf[0][16]));
 #pragma unroll
-            for (int g = 0; g < 3; ++g) {
-                PROF(1);
-                if (g == 0) GANTT(16);
-                mbar_wait(acc_full + g, it & 1);
-                tc_fence_after();
-                PROF(0);
-                GANTT(17 + 2 * g);
-#pragma unroll
-                for (int h = 0; h < kN / 16; ++h) {
-                    int32_t lo[16], hi[16];
-                    tmem_ld16(tlane + (2 * g) * kN + h * 16, lo);
-                    tmem_ld16(tlane + (2 * g + 1) * kN + h * 16, hi);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int n = 0; n < 16; ++n) {
-                        const int m = h * 16 + n;
-                        const int32_t qq = hi[n] * 256 + lo[n];          // |qq| < 2^30
-                        if (g == 0) {
-                            xl[m] = qq;
-                        } else if (g == 1) {
-                            const int64_t t = (int64_t)xl[m] + ((int64_t)qq << 16);
-                            xl[m] = (int32_t)(uint32_t)t;
-                            xh[m] = (int32_t)(t >> 32);
-                        } else {
-                            xh[m] += qq;
-                        }
+            for (int s = 0; s < kSteps; ++s) {
+                const int g = s / kH, h = s % kH;
+                tmem_ld_wait();                                  // buf[s & 1] has landed
+                if (h == kH - 1) {
+                    // every load of pair g is complete: hand the pair back to its MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    GANTT(18 + 2 * g);
+                    if (lane == 0) {
+                        mbar_arrive(acc_empty + g);
+                        // all MMAs of this tile have retired: its spike tile may be overwritten by the TMA
+                        if (g == 2 && warp == 4) mbar_arrive(b_empty + (uint32_t)it % kStages);
                     }
                 }
-                tc_fence_before();
-                __syncwarp();
-                GANTT(18 + 2 * g);
-                if (lane == 0) {
-                    mbar_arrive(acc_empty + g);                  // pair g is free for the next tile's MMAs
-                    // all MMAs of this tile have retired: its spike tile may be overwritten by the TMA
-                    if (g == 2 && warp == 4) mbar_arrive(b_empty + (uint32_t)it % kStages);
+                if (s + 1 < kSteps) {
+                    const int g2 = (s + 1) / kH, h2 = (s + 1) % kH;
+                    if (h2 == 0) {
+                        PROF(1);
+                        mbar_wait_probed(g2 == 1 ? probe1 : probe2, acc_full + g2, it & 1);
+                        PROF(4);
+                        tc_fence_after();
+                        PROF(5);
+                        GANTT(17 + 2 * g2);
+                    }
+                    tmem_ld16(tlane + (2 * g2) * kN + h2 * 16, reinterpret_cast<int32_t(&)[16]>(buf[(s + 1) & 1][0]));
+                    tmem_ld16(tlane + (2 * g2 + 1) * kN + h2 * 16, reinterpret_cast<int32_t(&)[16]>(buf[(s + 1) & 1][16]));
+                    if (s + 1 == 2 * kH) probe = mbar_probe(x_empty + (it & 1), ((it >> 1) & 1) ^ 1);
+                }
+#pragma unroll
+                for (int n = 0; n < 16; ++n) {
+                    const int m = h * 16 + n;
+                    const int32_t qq = buf[s & 1][16 + n] * 256 + buf[s & 1][n];          // |qq| < 2^30
+                    if (g == 0) {
+                        xl[m] = qq;
+                    } else if (g == 1) {
+                        const int64_t t = (int64_t)xl[m] + ((int64_t)qq << 16);
+                        xl[m] = (int32_t)(uint32_t)t;
+                        xh[m] = (int32_t)(t >> 32);
+                    } else {
+                        xh[m] += qq;
+                    }
                 }
             }
             // one rounding to fp32 (cvt.rn.f32.s64), exact power-of-two scale, hand over through TMEM
             const uint32_t xb = it & 1;
             PROF(1);
-            mbar_wait(x_empty + xb, ((it >> 1) & 1) ^ 1);
+            mbar_wait_probed(probe, x_empty + xb, ((it >> 1) & 1) ^ 1);
             tc_fence_after();
             PROF(2);
             GANTT(23);
+            probe0 = mbar_probe(acc_full + 0, (it + 1) & 1);        // next tile's first pair
 #pragma unroll
             for (int h = 0; h < kN / 16; ++h) {
                 float xf[16];
@@ -816,11 +861,12 @@ int snn_tc_output(SnnHandle *h, const int8_t *S1, int nb, int b0, int steps, flo
                 fprintf(stderr, "  gantt it=%d  mma:", 1000 + r);
                 for (int k = 0; k <= 14; ++k) fprintf(stderr, " %lld", g_[r * 48 + k] - t0_);
                 fprintf(stderr, "  | drain:");
-                for (int k = 16; k <= 24; ++k) fprintf(stderr, " %lld", g_[r * 48 + k] - t0_);
+                for (int k = 16; k <= 28; ++k) fprintf(stderr, " %lld", g_[r * 48 + k] - t0_);
                 fprintf(stderr, "  | scan:");
                 for (int k = 32; k <= 35; ++k) fprintf(stderr, " %lld", g_[r * 48 + k] - t0_);
                 fprintf(stderr, "\n");
             }
+            fprintf(stderr, "  drain detail: pair 1/2 mbar_wait %.0f  fence_after %.0f\n", avg[10], avg[11]);
             fprintf(stderr, "  scan : x_full-wait %.0f  other %.0f  load %.0f  chain %.0f\n", avg[12], avg[13], avg[14], avg[15]);
         }
     } prof_dump{prof_dev, grid.x, st, (long long)h->P_tiles * p.n_pairs * p.chunks / grid.x};
