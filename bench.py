@@ -302,7 +302,7 @@ def main():
                     traffic=load_traffic("output_tc_kernel", "streams=%d,queries=%d,places=%d,feature=%d" %
                                          (B, Q, P, F)),
                     peak_source=peaks["source"] + " bf16 sustained",
-                    kernel_ms=out_ms, feature_kernel_ms=ktime["feature_ms"] / max(ktime["n_feature"], 1),
+                    kernel_ms=out_ms, feature_ms_per_step=ktime["feature_ms"] / max(ktime["n_output"], 1),
                     share_of_step=ktime["output_ms"] / sum(ms),
                     algorithmic="2*F*P FLOP per query timestep (output layer); 2*I*F more in the feature kernel")
 

@@ -46,9 +46,12 @@ constexpr int kN = kTileRows;           // TMEM columns per plane: 2 streams x 3
 constexpr int kStages = 3;              // hidden-spike pair tiles in flight
 constexpr int kTmemCols = 512;          // 6 planes x 64 accumulator columns + 2 x 64 exchange columns
 constexpr int kXCol = kPlanes * kN;     // first exchange column
-constexpr int kThreads = 384;           // 3 warpgroups
-constexpr int kRegsControl = 56;        // setmaxnreg budgets: 128 * (56 + 224 + 152) <= 384 * 168
-constexpr int kRegsDrain = 224;
+constexpr int kDrainGroups = 2;         // drain warpgroups; each owns kN / kDrainGroups accumulator columns
+constexpr int kNd = kN / kDrainGroups;  // (= the 32 steps of one stream)
+constexpr int kScanWarp0 = 4 + 4 * kDrainGroups;
+constexpr int kThreads = 128 * (2 + kDrainGroups);   // control + drain warpgroups + scan
+constexpr int kRegsControl = 56;        // setmaxnreg budgets: 128 * (56 + 2 * 152 + 152) = 512 * 128
+constexpr int kRegsDrain = 152;
 constexpr int kRegsScan = 152;
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
@@ -302,9 +305,9 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
         for (int i = 0; i < kStages; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
         for (int i = 0; i < 3; ++i) {
             mbar_init(acc_full + i, 1);
-            mbar_init(acc_empty + i, 4);  // one arrival per drain warp
+            mbar_init(acc_empty + i, 4 * kDrainGroups);  // one arrival per drain warp
         }
-        for (int i = 0; i < 2; ++i) { mbar_init(x_full + i, 4); mbar_init(x_empty + i, 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(x_full + i, 4 * kDrainGroups); mbar_init(x_empty + i, 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {   // TMEM allocation (whole warp), address lands in shared memory
@@ -413,11 +416,12 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
         }
         if (warp == 1) PROF_FLUSH(0);
     }
-    } else if (warp < 8) {
-        // ===================== drain warpgroup: TMEM accumulators -> exact fp32 contraction results ==========
+    } else if (warp < kScanWarp0) {
+        // ===================== drain warpgroups: TMEM accumulators -> exact fp32 contraction results =========
+        // warpgroup dw owns columns [dw * kNd, (dw + 1) * kNd) of every plane (the 32 steps of stream dw)
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsDrain));
         const int quarter = warp & 3;                          // TMEM lanes this warp may touch
-        const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((warp - 4) >> 2) * kNd;
         int it = 0;
         uint32_t probe0 = 0;
         PROF_DECL;
@@ -425,13 +429,13 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
         const int place = (item / p.n_pairs) * kM + quarter * 32 + lane;
         const float scale = place < p.P ? p.scale[place] : 0.0f;
         for (int c = 0; c < p.chunks; ++c, ++it) {
-            // X = sum_j P_j 256^j as (xh:xl) for the 64 columns of this lane.  The 12 (pair, 16-column) loads
+            // X = sum_j P_j 256^j as (xh:xl) for the kNd columns of this lane.  The (pair, 16-column) loads
             // are double-buffered in registers: the tcgen05.ld of step s + 1 is in flight while step s is
             // folded into X, so only the first load's latency is exposed.
-            int32_t xl[kN], xh[kN];
+            int32_t xl[kNd], xh[kNd];
             int32_t buf[2][32];
             uint32_t probe = 0;
-            constexpr int kH = kN / 16, kSteps = 3 * kH;
+            constexpr int kH = kNd / 16, kSteps = 3 * kH;
             PROF(1);
             GANTT(16);
             mbar_wait_probed(probe0, acc_full + 0, it & 1);
@@ -496,7 +500,7 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
             GANTT(23);
             probe0 = mbar_probe(acc_full + 0, (it + 1) & 1);        // next tile's first pair
 #pragma unroll
-            for (int h = 0; h < kN / 16; ++h) {
+            for (int h = 0; h < kNd / 16; ++h) {
                 float xf[16];
 #pragma unroll
                 for (int n = 0; n < 16; ++n) {
@@ -516,7 +520,7 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
         if (warp == 4) PROF_FLUSH(6);
     } else {
         // ===================== scan warpgroup: IAF#2 recurrence of both streams, spike counts ================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsScan));
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsScan));
         const int quarter = warp & 3;
         const float thr = p.thr, vmin = p.vmin;
         const int Q = p.steps / p.T;
@@ -560,7 +564,7 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
                 // hidden layer: this tile's spike bytes are staged in shared memory [kc][row = stream*32+n][16]
                 uint8_t *stage_out = sOut + (it & 1) * 8192 + (quarter * 2 + (lane >> 4)) * 1024 + (lane & 15);
                 if (kHidden) {
-                    if (warp == 8 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    if (warp == kScanWarp0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                     asm volatile("bar.sync 1, 128;" ::: "memory");   // staging buffer (it & 1) is free again
                 }
 
@@ -673,7 +677,7 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
                     // neuron tile (contiguous in the pair-tile layout) with one bulk store
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     asm volatile("bar.sync 1, 128;" ::: "memory");
-                    if (warp == 8 && lane == 0) {
+                    if (warp == kScanWarp0 && lane == 0) {
                         const int kc0 = tile * 8, nkc = min(8, p.out_Fp / 16 - kc0);
                         if (nkc > 0)
                             bulk_s2g(p.S1_out + ((size_t)pr * p.chunks + c) * ((size_t)kN * p.out_Fp) + (size_t)kc0 * 1024,
@@ -685,9 +689,9 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
             if (live0) p.v2[(size_t)b0 * p.P + place] = v0;
             if (live1) p.v2[(size_t)b1 * p.P + place] = v1;
         }
-        if (warp == 8) PROF_FLUSH(12);
+        if (warp == kScanWarp0) PROF_FLUSH(12);
         if (kHidden) {
-            if (warp == 8 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            if (warp == kScanWarp0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
             if (n_over) atomicAdd((unsigned long long *)p.overflow, (unsigned long long)n_over);
         }
     }
