@@ -579,35 +579,43 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
                     const int nb = p.T - 1 - t_in_q;             // tile-local index of the query's last step
                     const float s0 = v0, s1 = v1;
                     float all0 = 0.0f, head0 = 0.0f, all1 = 0.0f, head1 = 0.0f;
-                    bool multi0 = false, multi1 = false;
+                    // the largest pre-spike potential of the tile decides afterwards whether a step overflowed
+                    // the fast path (one FMNMX per step instead of a compare and a predicate OR)
+                    float amax0 = -1.0f, amax1 = -1.0f;
+                    bool multi0, multi1;
                     if (kHidden) {
                         // Hidden layer: several spikes per step do occur (~3e-4 of neuron-steps), so the count is
-                        // computed exactly on the ALU in every step: for 0 <= m < 2^23, fl_rz(m + 2^23) - 2^23 is
-                        // trunc(m), and the low byte of fl_rz(m + 2^23) is the spike count itself.
+                        // computed exactly on the ALU in every step: for 0 <= m < 2^23, t = fl_rz(m + 2^23) is
+                        // 2^23 + trunc(m), its low byte is the spike count s itself, and (2^23 + 1) - t = 1 - s.
 #pragma unroll
                         for (int n = 0; n < kTileSteps; ++n) {
                             const float a = __fadd_rn(v0, x[n]), b = __fadd_rn(v1, x[kTileSteps + n]);
                             const float ta = __fadd_rz(fmaxf(a, 0.0f), 8388608.0f), tb = __fadd_rz(fmaxf(b, 0.0f), 8388608.0f);
-                            const float sa = __fsub_rn(ta, 8388608.0f), sb = __fsub_rn(tb, 8388608.0f);   // trunc, exact
-                            multi0 |= (a >= 128.0f); multi1 |= (b >= 128.0f);     // beyond LENS_MAX_SPIKE: generic path
+                            amax0 = fmaxf(amax0, a); amax1 = fmaxf(amax1, b);
                             // v - s is exact, so relu(v - s + 1) - 1 rounds like the reference's three operations
-                            v0 = __fadd_rn(fmaxf(__fadd_rn(a, __fsub_rn(1.0f, sa)), 0.0f), -1.0f);
-                            v1 = __fadd_rn(fmaxf(__fadd_rn(b, __fsub_rn(1.0f, sb)), 0.0f), -1.0f);
+                            v0 = __fadd_rn(fmaxf(__fadd_rn(a, __fsub_rn(8388609.0f, ta)), 0.0f), -1.0f);
+                            v1 = __fadd_rn(fmaxf(__fadd_rn(b, __fsub_rn(8388609.0f, tb)), 0.0f), -1.0f);
                             stage_out[n * 16] = (uint8_t)__float_as_uint(ta);
                             stage_out[512 + n * 16] = (uint8_t)__float_as_uint(tb);
                         }
+                        multi0 = amax0 >= 128.0f; multi1 = amax1 >= 128.0f;   // beyond LENS_MAX_SPIKE: generic path
                     } else {
+                        // spikes are collected as one bit per step; the counts are popcounts of the masks
+                        uint32_t m0 = 0u, m1 = 0u;
 #pragma unroll
-                    for (int n = 0; n < kTileSteps; ++n) {
-                        const float a = __fadd_rn(v0, x[n]), b = __fadd_rn(v1, x[kTileSteps + n]);
-                        const float sa = (a >= 1.0f) ? 1.0f : 0.0f, sb = (b >= 1.0f) ? 1.0f : 0.0f;
-                        const float ca = (a >= 1.0f) ? 0.0f : 1.0f, cb = (b >= 1.0f) ? 0.0f : 1.0f;   // 1 - s
-                        multi0 |= (a >= 2.0f); multi1 |= (b >= 2.0f);
-                        v0 = __fadd_rn(fmaxf(__fadd_rn(a, ca), 0.0f), -1.0f);
-                        v1 = __fadd_rn(fmaxf(__fadd_rn(b, cb), 0.0f), -1.0f);
-                        all0 += sa; all1 += sb;
-                        if (n <= nb) { head0 += sa; head1 += sb; }
-                    }
+                        for (int n = 0; n < kTileSteps; ++n) {
+                            const float a = __fadd_rn(v0, x[n]), b = __fadd_rn(v1, x[kTileSteps + n]);
+                            const float ca = (a >= 1.0f) ? 0.0f : 1.0f, cb = (b >= 1.0f) ? 0.0f : 1.0f;   // 1 - s
+                            if (a >= 1.0f) m0 |= 1u << n;
+                            if (b >= 1.0f) m1 |= 1u << n;
+                            amax0 = fmaxf(amax0, a); amax1 = fmaxf(amax1, b);
+                            v0 = __fadd_rn(fmaxf(__fadd_rn(a, ca), 0.0f), -1.0f);
+                            v1 = __fadd_rn(fmaxf(__fadd_rn(b, cb), 0.0f), -1.0f);
+                        }
+                        multi0 = amax0 >= 2.0f; multi1 = amax1 >= 2.0f;
+                        const uint32_t head_mask = nb >= kTileSteps - 1 ? 0xffffffffu : ((2u << nb) - 1u);
+                        all0 = (float)__popc(m0); head0 = (float)__popc(m0 & head_mask);
+                        all1 = (float)__popc(m1); head1 = (float)__popc(m1 & head_mask);
                     }
                     const bool boundary = nb < kTileSteps;
                     if (kHidden) {
@@ -828,6 +836,47 @@ void snn_tc_release(SnnHandle *h)
         tc::output_tc_kernel<U, D, K, H><<<grid, tc::kThreads, smem, st>>>(p);                                       \
     } while (0)
 
+#ifdef LENS_TC_PROFILE
+struct ProfDump {
+    long long *d; unsigned n; cudaStream_t st; long long iters; const char *name;
+    static long long *buffer()
+    {
+        static long long *dev = nullptr;
+        if (!dev) cudaMalloc(&dev, (1024 * 24 + 256) * sizeof(long long));
+        return dev;
+    }
+    ProfDump(unsigned n_, cudaStream_t st_, long long iters_, const char *name_) : d(buffer()), n(n_), st(st_), iters(iters_), name(name_)
+    {
+        cudaMemsetAsync(d, 0, (1024 * 24 + 256) * sizeof(long long), st);
+    }
+    ~ProfDump()
+    {
+        std::vector<long long> hbuf(n * 24);
+        cudaStreamSynchronize(st);
+        cudaMemcpy(hbuf.data(), d, hbuf.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        double avg[18] = {0};
+        for (unsigned b = 0; b < n; ++b) for (int i = 0; i < 18; ++i) avg[i] += (double)hbuf[b * 24 + i] / n / iters;
+        fprintf(stderr, "[tc-prof %s] clk per tile-iteration (avg over %u CTAs, %lld iters/CTA)\n", name, n, iters);
+        fprintf(stderr, "  mma  : planes-wait %.0f  b_full-wait %.0f  acc_empty-wait %.0f  issue %.0f\n", avg[0], avg[1], avg[2], avg[3]);
+        fprintf(stderr, "  drain: acc_full-wait %.0f  fold %.0f  x_empty-wait %.0f  convert+st %.0f  pair 1/2 wait %.0f  fence %.0f\n",
+                avg[6], avg[7], avg[8], avg[9], avg[10], avg[11]);
+        fprintf(stderr, "  scan : x_full-wait %.0f  other %.0f  load %.0f  chain %.0f\n", avg[12], avg[13], avg[14], avg[15]);
+        long long g_[144];
+        cudaMemcpy(g_, d + 1024 * 24, sizeof(g_), cudaMemcpyDeviceToHost);
+        const long long t0_ = g_[0];
+        for (int r = 0; r < 3; ++r) {
+            fprintf(stderr, "  gantt it=%d  mma:", 1000 + r);
+            for (int k = 0; k <= 14; ++k) fprintf(stderr, " %lld", g_[r * 48 + k] - t0_);
+            fprintf(stderr, "  | drain:");
+            for (int k = 16; k <= 24; ++k) fprintf(stderr, " %lld", g_[r * 48 + k] - t0_);
+            fprintf(stderr, "  | scan:");
+            for (int k = 32; k <= 35; ++k) fprintf(stderr, " %lld", g_[r * 48 + k] - t0_);
+            fprintf(stderr, "\n");
+        }
+    }
+};
+#endif
+
 int snn_tc_output(SnnHandle *h, const int8_t *S1, int nb, int b0, int steps, float *counts,
                   uint8_t *out_steps, cudaStream_t st)
 {
@@ -842,38 +891,8 @@ int snn_tc_output(SnnHandle *h, const int8_t *S1, int nb, int b0, int steps, flo
     const size_t smem = tc::smem_bytes(h->Fp);
     dim3 grid((unsigned)std::min<long long>(sms, (long long)h->P_tiles * p.n_pairs));
 #ifdef LENS_TC_PROFILE
-    static long long *prof_dev = nullptr;
-    if (!prof_dev) cudaMalloc(&prof_dev, (1024 * 24 + 256) * sizeof(long long));
-    cudaMemsetAsync(prof_dev, 0, (1024 * 24 + 256) * sizeof(long long), st);
-    p.prof = prof_dev;
-    struct ProfDump {
-        long long *d; unsigned n; cudaStream_t st; long long iters;
-        ~ProfDump()
-        {
-            std::vector<long long> hbuf(n * 24);
-            cudaStreamSynchronize(st);
-            cudaMemcpy(hbuf.data(), d, hbuf.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-            double avg[18] = {0};
-            for (unsigned b = 0; b < n; ++b) for (int i = 0; i < 18; ++i) avg[i] += (double)hbuf[b * 24 + i] / n / iters;
-            fprintf(stderr, "[tc-prof] clk per tile-iteration (avg over %u CTAs, %lld iters/CTA)\n", n, iters);
-            fprintf(stderr, "  mma  : planes-wait %.0f  b_full-wait %.0f  acc_empty-wait %.0f  issue %.0f\n", avg[0], avg[1], avg[2], avg[3]);
-            fprintf(stderr, "  drain: acc_full-wait %.0f  fold %.0f  x_empty-wait %.0f  convert+st %.0f\n", avg[6], avg[7], avg[8], avg[9]);
-            long long g_[144];
-            cudaMemcpy(g_, d + 1024 * 24, sizeof(g_), cudaMemcpyDeviceToHost);
-            const long long t0_ = g_[0];
-            for (int r = 0; r < 3; ++r) {
-                fprintf(stderr, "  gantt it=%d  mma:", 1000 + r);
-                for (int k = 0; k <= 14; ++k) fprintf(stderr, " %lld", g_[r * 48 + k] - t0_);
-                fprintf(stderr, "  | drain:");
-                for (int k = 16; k <= 28; ++k) fprintf(stderr, " %lld", g_[r * 48 + k] - t0_);
-                fprintf(stderr, "  | scan:");
-                for (int k = 32; k <= 35; ++k) fprintf(stderr, " %lld", g_[r * 48 + k] - t0_);
-                fprintf(stderr, "\n");
-            }
-            fprintf(stderr, "  drain detail: pair 1/2 mbar_wait %.0f  fence_after %.0f\n", avg[10], avg[11]);
-            fprintf(stderr, "  scan : x_full-wait %.0f  other %.0f  load %.0f  chain %.0f\n", avg[12], avg[13], avg[14], avg[15]);
-        }
-    } prof_dump{prof_dev, grid.x, st, (long long)h->P_tiles * p.n_pairs * p.chunks / grid.x};
+    ProfDump prof_dump(grid.x, st, (long long)h->P_tiles * p.n_pairs * p.chunks / grid.x, "output");
+    p.prof = prof_dump.d;
 #endif
     LaunchTimer timer(h, st, 1);
     const bool unit = h->thr == 1.0f && h->vmin == -1.0f, dbg = out_steps != nullptr;
@@ -919,15 +938,14 @@ int snn_tc_hidden(SnnHandle *h, const uint8_t *pooled, int nb, int b0, int steps
     p.P = h->F; p.Fp = h->Ip; p.T = h->T; p.steps = steps; p.chunks = chunks; p.nb = nb; p.n_pairs = n_pairs;
     p.thr = h->thr; p.vmin = h->vmin;
     p.S1_out = h->S1; p.out_Fp = h->Fp; p.overflow = h->counters;
-#ifdef LENS_TC_PROFILE
-    static long long *prof_dev_h = nullptr;
-    if (!prof_dev_h) cudaMalloc(&prof_dev_h, (1024 * 24 + 256) * sizeof(long long));
-    p.prof = prof_dev_h;
-#endif
     const int sms = std::max(sm_count(), 1);
     p.n_tiles = h->F_tiles;
     const size_t smem = tc::smem_bytes(h->Ip, true);
     dim3 grid((unsigned)std::min<long long>(sms, (long long)h->F_tiles * p.n_pairs));
+#ifdef LENS_TC_PROFILE
+    ProfDump prof_dump(grid.x, st, (long long)h->F_tiles * p.n_pairs * p.chunks / grid.x, "hidden");
+    p.prof = prof_dump.d;
+#endif
     LaunchTimer timer(h, st, 0);
     const bool dbg = hidden_steps != nullptr;
     if (h->Ip == 128) { if (dbg) LENS_TC_LAUNCH_K(true, true, 4, true); else LENS_TC_LAUNCH_K(true, false, 4, true); }
