@@ -135,3 +135,86 @@ def test_forward_range_equals_full_forward():
     assert torch.equal(full, parts)
     for x, y in zip(a.state(), b.state()):
         assert torch.equal(x, y)
+
+
+def test_config3_full_size_properties():
+    """BASELINE.json configs[2] at its full size on one GPU: 65 536 streams x 10 queries x 250 steps,
+    P = 10 000, L = 10 (1.64e8 query timesteps, 26 GB of spike counts).  Checked through properties that
+    need no oracle: planted duplicate streams give identical rows, a sample of streams equals the
+    event-driven CUDA-core path bit for bit, the top-N lists are ordered and consistent with D."""
+    from lens_b200 import ops
+    P, B, Q, L, N = 10000, 65536, 10, 10, 25
+    g = torch.Generator(device="cuda").manual_seed(17)
+    # pixel counts: ~40 % zeros, otherwise 0..44 (same order of magnitude as synth.pixel_counts), made on the GPU
+    pooled = torch.randint(0, 45, (B, Q, 100), device="cuda", generator=g, dtype=torch.int32)
+    pooled = torch.where(torch.rand((B, Q, 100), device="cuda", generator=g) < 0.4, 0, pooled).to(torch.uint8)
+    src = torch.tensor([3, 1000, 40000, 65535], device="cuda")
+    dup = torch.tensor([65000, 7, 12345, 0], device="cuda")
+    pooled[dup] = pooled[src]
+    net = make_net(P, B)
+    S = net.run_streams(pooled=pooled, mode=2)
+    assert S.shape == (B, Q, P) and net.overflow() == 0
+    assert torch.equal(S[dup], S[src])
+    sample = torch.tensor([0, 3, 4097, 32768, 65535], device="cuda")
+    ref = make_net(P, len(sample)).run_streams(pooled=pooled[sample].contiguous(), mode=1)
+    assert torch.equal(S[sample], ref)
+    assert float(S[sample].sum()) > 0
+    tv, ti, _ = ops.seqmatch_topk(S, L, N)
+    Qo, Po = Q - L + 1, P - L + 1
+    assert tv.shape == (B, Qo, N) and int(ti.min()) >= 0 and int(ti.max()) < Po
+    assert bool((tv[..., :-1] >= tv[..., 1:]).all())
+    # the best value of a sampled stream equals the maximum of its sequence-matched column
+    _, _, D = ops.seqmatch_topk(S[sample].contiguous(), L, N, want_D=True)
+    assert torch.equal(D.amax(dim=1), tv[sample][..., 0])
+    del S, tv, ti, D, net
+    torch.cuda.empty_cache()
+
+
+def test_config4_full_size_binning():
+    """BASELINE.json configs[3]: 1e9 events on the 128x128 sensor, 250 ms windows.  Checksum of checksums:
+    every frame's pixel sum equals the window's event count modulo 256, the window counts add up to the
+    number of events, and binning the two halves of the stream separately adds up to the whole (mod 256)."""
+    from lens_b200 import ops
+    n, window_us = 1_000_000_000, 250_000
+    g = torch.Generator(device="cuda").manual_seed(23)
+    # ascending timestamps with ~131 k events per window: increments 0..3 us (mean 1.9 us); cumsum stays < 2^32
+    t = torch.randint(0, 4, (n,), device="cuda", generator=g, dtype=torch.int32)
+    t[::2] += 1
+    t = torch.cumsum(t, 0, dtype=torch.int64)
+    n_win = int(t[-1].item()) // window_us + 1
+    assert int(t[-1].item()) < 2 ** 32
+    t = t.to(torch.uint32).view(torch.int32)
+    x = torch.randint(0, 128, (n,), device="cuda", generator=g, dtype=torch.int16)
+    y = torch.randint(0, 128, (n,), device="cuda", generator=g, dtype=torch.int16)
+    f, p, c = ops.bin_events(t, x, y, 0, window_us, n_win, 128, 8)
+    assert int(c.sum()) == n and n_win > 7000
+    sums = f.view(n_win, -1).to(torch.int64).sum(1)
+    assert torch.equal(sums % 256, c.to(torch.int64) % 256)
+    assert torch.equal(p, ops.pool_frames(f, 8))
+    h = n // 2 + 12344                      # multiple of 8: the library wants 16-byte aligned x / y
+    fa, _, ca = ops.bin_events(t[:h].contiguous(), x[:h].contiguous(), y[:h].contiguous(), 0, window_us, n_win, 128, 8)
+    fb, _, cb = ops.bin_events(t[h:].contiguous(), x[h:].contiguous(), y[h:].contiguous(), 0, window_us, n_win, 128, 8)
+    assert torch.equal(c, ca + cb)
+    assert torch.equal(f, (fa.to(torch.int32) + fb.to(torch.int32)).remainder(256).to(torch.uint8))
+    del t, x, y, f, fa, fb
+    torch.cuda.empty_cache()
+
+
+def test_config5_shard_properties():
+    """BASELINE.json configs[4], one rank's shard: 1 024 streams against the full 100 000-place database
+    (Q = 10, L = 10, N = 25).  Same oracle-free properties as config 3."""
+    from lens_b200 import ops
+    P, B, Q, L, N = 100000, 1024, 10, 10, 25
+    pooled = cuda(synth.pixel_counts((B, Q, 100), seed=31))
+    pooled[1000] = pooled[17]
+    net = make_net(P, B)
+    S = net.run_streams(pooled=pooled, mode=2)
+    assert net.overflow() == 0 and torch.equal(S[1000], S[17])
+    sample = torch.tensor([0, 17, 1023], device="cuda")
+    ref = make_net(P, len(sample)).run_streams(pooled=pooled[sample].contiguous(), mode=1)
+    assert torch.equal(S[sample], ref) and float(ref.sum()) > 0
+    tv, ti, _ = ops.seqmatch_topk(S, L, N)
+    assert int(ti.min()) >= 0 and int(ti.max()) < P - L + 1 and bool((tv[..., :-1] >= tv[..., 1:]).all())
+    _, _, D = ops.seqmatch_topk(S[sample].contiguous(), L, N, want_D=True)
+    assert torch.equal(D.amax(dim=1), tv[sample][..., 0])
+    assert torch.equal(torch.gather(D, 1, ti[sample].long().transpose(1, 2)).transpose(1, 2), tv[sample])
