@@ -564,8 +564,10 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
                 // hidden layer: this tile's spike bytes are staged in shared memory [kc][row = stream*32+n][16]
                 uint8_t *stage_out = sOut + (it & 1) * 8192 + (quarter * 2 + (lane >> 4)) * 1024 + (lane & 15);
                 if (kHidden) {
-                    if (warp == kScanWarp0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                    asm volatile("bar.sync 1, 128;" ::: "memory");   // staging buffer (it & 1) is free again
+                    // every scan warp ships its own 32 neurons (two 1 KB k-chunks), so the staging buffers need
+                    // warp-level synchronisation only: this warp's store of two tiles ago has been read
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    __syncwarp();
                 }
 
                 const int t_base = c * kTileSteps;
@@ -681,15 +683,15 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
                 while (t_in_q >= p.T) { t_in_q -= p.T; ++q; }
                 if (kHidden) {
                     for (int n = nvalid; n < kTileSteps; ++n) { stage_out[n * 16] = 0; stage_out[512 + n * 16] = 0; }
-                    // generic-proxy writes -> async proxy, then one thread ships the tile's rows of this
-                    // neuron tile (contiguous in the pair-tile layout) with one bulk store
+                    // generic-proxy writes -> async proxy, then one lane ships the warp's two k-chunks of the
+                    // tile (contiguous in the pair-tile layout) with one bulk store
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                    if (warp == kScanWarp0 && lane == 0) {
-                        const int kc0 = tile * 8, nkc = min(8, p.out_Fp / 16 - kc0);
+                    __syncwarp();
+                    if (lane == 0) {
+                        const int kcw = tile * 8 + quarter * 2, nkc = min(2, p.out_Fp / 16 - kcw);
                         if (nkc > 0)
-                            bulk_s2g(p.S1_out + ((size_t)pr * p.chunks + c) * ((size_t)kN * p.out_Fp) + (size_t)kc0 * 1024,
-                                     sOut + (it & 1) * 8192, (uint32_t)nkc * 1024u);
+                            bulk_s2g(p.S1_out + ((size_t)pr * p.chunks + c) * ((size_t)kN * p.out_Fp) + (size_t)kcw * 1024,
+                                     sOut + (it & 1) * 8192 + quarter * 2048, (uint32_t)nkc * 1024u);
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                 }
@@ -699,7 +701,7 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
         }
         if (warp == kScanWarp0) PROF_FLUSH(12);
         if (kHidden) {
-            if (warp == kScanWarp0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
             if (n_over) atomicAdd((unsigned long long *)p.overflow, (unsigned long long)n_over);
         }
     }
