@@ -21,16 +21,20 @@
 // a cp.async.bulk (TMA) ring.  TMEM holds the 6 x 64-column int32 accumulator set plus two 64-column
 // fp32 exchange buffers (512 columns in total).
 //
-// Three warpgroups, registers redistributed with setmaxnreg:
-//   control  warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (warps 2-3 idle),
-//   drain    warps 4-7: tcgen05.ld the accumulators plane pair by plane pair (each pair goes back to the
-//            MMA warp as soon as it is read), recombine X = sum_j P_j 256^j in int64, round once to fp32,
-//            scale, tcgen05.st the 64 contraction results of every place into an exchange buffer,
-//   scan     warps 8-11: tcgen05.ld the results and run the serial IAF#2 recurrence of BOTH streams of the
-//            pair as two interleaved dependency chains (FADD -> FSET -> FADD -> FMNMX -> FADD per step),
-//            spike counts per query.
-// The serial chain (~830 cycles per tile) and the parallel drain/convert work (~900 cycles) thus overlap
-// with each other and with the MMAs of the next tile (~1950 cycles, shared-memory operand bound).
+// Four warpgroups (512 threads), registers redistributed with setmaxnreg (56 / 152 / 152 / 152):
+//   control  warp 0 = TMA producer; warps 1-3 = MMA issuers, one per plane pair (warp 1 also allocates
+//            TMEM): the ~450 cycles a warp spends per pair in tcgen05.commit and in waiting for the pair's
+//            accumulators to come back overlap the other two warps' MMAs,
+//   drain    warps 4-7 (columns 0..31 = even stream) and 8-11 (columns 32..63 = odd stream): tcgen05.ld the
+//            accumulators plane pair by plane pair with register double buffering (each pair goes back to
+//            its MMA warp as soon as its last load has landed), recombine X = sum_j P_j 256^j in int64,
+//            round once to fp32, scale, tcgen05.st the contraction results into an exchange buffer,
+//   scan     warps 12-15: tcgen05.ld the 64 results of every place and run the serial IAF#2 recurrence of
+//            BOTH streams of the pair as two interleaved dependency chains (FADD -> FSET -> FADD -> FMNMX
+//            -> FADD per step), spike bits per step, popcounts per query.
+// With this split the kernel runs at the tensor pipe's floor for N = 64 (42 MMAs x 48 cycles, bound by
+// the shared-memory operand fetch, plus three commits): ~2400 cycles per tile.  -DLENS_TC_PROFILE builds
+// an instrumented variant (phase clocks + a Gantt chart of three tiles; profiles/r01_tc_phase_profile.md).
 #include "snn.cuh"
 
 #include <algorithm>
@@ -157,18 +161,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int32_t (&r)[16])
         "%14, %15}, [%16];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-}
-// 32 consecutive 32-bit columns of this thread's TMEM lane
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, int32_t (&r)[32])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
-        "%14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
 }
 // store 16 consecutive 32-bit columns of this thread's TMEM lane
