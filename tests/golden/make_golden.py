@@ -225,6 +225,58 @@ def run_case(stub, name, argv, out_path, full_steps=2):
     return R
 
 
+def run_options(stub, out_path):
+    """The tail of evaluate() (sequence matching, GT slicing/dilation, Recall@N) for other option values:
+    the reference's whole run_inference on the bundled example with --sequence_length / --GT_tolerance varied.
+    Stores D (what the reference hands to recallAtK), GTtol and R per variant, or the exception it raises."""
+    import main as ref_main
+    from lens.run_model import LENS, run_inference
+    import lens.run_model as rm
+    out = {}
+    variants = [(0, 3), (1, 3), (2, 0), (2, 1), (3, 3), (4, 2), (10, 3), (25, 5)]
+    for L, tol in variants:
+        argv = ["--sim_mat", "--matching", "--nocuda", "--sequence_length", str(L), "--GT_tolerance", str(tol)]
+        captured = {}
+        orig_init = ref_main.initialize_and_run_model
+        ref_main.initialize_and_run_model = lambda a: captured.setdefault("args", a)
+        old_argv = sys.argv
+        sys.argv = ["main.py"] + argv
+        try:
+            ref_main.parse_network()
+        finally:
+            sys.argv = old_argv
+            ref_main.initialize_and_run_model = orig_init
+        args = captured["args"]
+        rec = {}
+        real_recall = rm.recallAtK
+
+        def recallAtK(S, GT, GTsoft=None, K=1, rec=rec, real_recall=real_recall):
+            rec["D"] = np.array(S)
+            rec["GTtol"] = np.array(GT)
+            return real_recall(S, GT, GTsoft, K=K)
+        rm.recallAtK = recallAtK
+        key = f"L{L}_tol{tol}"
+        try:
+            model = LENS(args)
+            torch.set_num_threads(1)
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                R = run_inference(model, ref_main.generate_model_name(model))
+            out[key + "/D"] = rec["D"].astype(np.float32)
+            out[key + "/GTtol"] = rec["GTtol"].astype(np.uint8)
+            out[key + "/R"] = np.array(R, dtype=np.float64)
+            out[key + "/error"] = np.array("")
+            print(f"[options {key}] D{rec['D'].shape} GTtol{rec['GTtol'].shape} R={R}")
+        except Exception as e:          # noqa: BLE001 - the outcome itself is the fixture
+            out[key + "/error"] = np.array(type(e).__name__ + ": " + str(e)[:200])
+            print(f"[options {key}] raised {type(e).__name__}: {e}")
+        finally:
+            rm.recallAtK = real_recall
+    out["variants"] = np.array(variants)
+    np.savez_compressed(out_path, **out)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -247,6 +299,8 @@ def main():
         if a.only and a.only != name:
             continue
         run_case(stub, name, argv, os.path.join(HERE, name + ".npz"))
+    if not a.only or a.only == "options":
+        run_options(stub, os.path.join(HERE, "options.npz"))
 
 
 if __name__ == "__main__":

@@ -210,3 +210,32 @@ def test_online_matcher_matches_reference_arithmetic():
                 assert np.array_equal(a[1].cpu().numpy(), ref)
         assert n_match == 2
         assert np.array_equal(gpu.similarity_matrix().cpu().numpy(), cpu.matrix.T)
+
+
+def test_evaluate_option_space(example_tree, monkeypatch):
+    """LENS.evaluate with other --sequence_length / --GT_tolerance values == the reference's own run on
+    the bundled example (tests/golden/options.npz): D and GTtol identical, Recall@N within the tie bounds
+    and equal to the deterministic rule; --sequence_length 1 fails with the reference's assertion."""
+    from lens_b200.config import default_args, generate_model_name
+    from lens_b200.run_model import LENS, run_inference
+    opt = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "options.npz"))
+    g, root = example_tree("config1", "example", "davis128", "example-reference", "example-query")
+    monkeypatch.chdir(root.parent)
+    for L, tol in opt["variants"]:
+        key = f"L{L}_tol{tol}"
+        args = default_args(matching=True, sim_mat=True, data_dir=str(root / "dataset") + "/",
+                            sequence_length=int(L), GT_tolerance=int(tol))
+        args.quiet = True
+        model = LENS(args)
+        name = generate_model_name(model)
+        if str(opt[key + "/error"]):
+            with pytest.raises(AssertionError, match="same shape"):
+                run_inference(model, name, models_dir=str(root / "models"))
+            continue
+        R = run_inference(model, name, models_dir=str(root / "models"))
+        assert np.array_equal(np.asarray(model.dist_matrix_seq, dtype=np.float32), opt[key + "/D"]), key
+        assert np.array_equal(model.GTtol, opt[key + "/GTtol"]), key
+        for got, want, K in zip(R, opt[key + "/R"], (1, 5, 10, 15, 20, 25)):
+            lo, hi = O.recall_bounds(opt[key + "/D"], model.GTtol, K)
+            assert round(lo, 2) <= want <= round(hi, 2) and round(lo, 2) <= got <= round(hi, 2), (key, K)
+            assert got == round(O.recall_at_k(opt[key + "/D"], model.GTtol, K=K, kind="stable"), 2), (key, K)

@@ -290,3 +290,28 @@ def test_dataset_csv_matches_reference_writer(tmp_path):
     create_csv_from_images(str(tmp_path), str(out))
     assert open(out).read() == str(g["plain/csv"])        # the golden was read in text mode too
     assert abs(haversine(153.0, -27.5, 153.0, -27.5)) == 0 and 110e3 < haversine(153.0, -27.0, 153.0, -28.0) < 112e3
+
+
+def test_evaluate_tail_option_space(golden):
+    """Sequence matching, GT slicing / dilation and Recall@N for other --sequence_length / --GT_tolerance
+    values, against the reference's own run on the bundled example (tests/golden/options.npz)."""
+    g = np.load(os.path.join(GOLDEN, "options.npz"))
+    c1 = golden("config1")
+    S, GT = c1["S"].astype(np.float64), c1["GT"]
+    n = 0
+    for L, tol in g["variants"]:
+        key = f"L{L}_tol{tol}"
+        if str(g[key + "/error"]):
+            assert L == 1 and "same shape" in str(g[key + "/error"])
+            D, GTtol = O.seqmatch(S, L), O.make_gt_tol(GT, L, tol)
+            assert D.shape != GTtol.shape          # the reference's assertion fires for the same reason
+            continue
+        D, GTtol, R = O.evaluate_tail(S, GT, int(L), int(tol))
+        assert np.array_equal(D.astype(np.float32), g[key + "/D"]), key
+        assert np.array_equal(GTtol, g[key + "/GTtol"]), key
+        for got, want, K in zip(R, g[key + "/R"], (1, 5, 10, 15, 20, 25)):
+            lo, hi = O.recall_bounds(D, GTtol, K)
+            assert round(lo, 2) <= want <= round(hi, 2), (key, K)       # tie-aware bounds hold for the reference
+            assert got == want, (key, K)                                  # same numpy, same unstable argsort
+        n += 1
+    assert n == 7
