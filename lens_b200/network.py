@@ -42,6 +42,8 @@ class B200Network:
         if not torch.cuda.is_available():
             raise LensError("B200Network needs a CUDA device; there is no CPU fallback")
         self.device = torch.device(device if device is not None else "cuda")
+        if self.device.type != "cuda":
+            raise LensError(f"B200Network lives on a CUDA device, not on '{self.device}'")
         self.roi, self.k, self.T = int(roi), int(k), int(num_timesteps)
         self.dims, self.c = pool_geometry(self.roi, self.k)
         self.W_feat = W_feat.detach().to(self.device, torch.float32).contiguous()
