@@ -8,7 +8,6 @@ decoding and the natural sort of file names stay on the host; the plots of the r
 import os
 import re
 
-import numpy as np
 import torch
 
 from .. import ops

@@ -16,7 +16,6 @@ the float parsing is part of what is pinned), the hot pixels, the reference's ra
 (unique_indices / centroid dictionary) and every frame the reference wrote, for several argument sets.
 """
 import argparse
-import io
 import json
 import os
 import sys

@@ -11,7 +11,6 @@ row-sharded place database (config 5 of BASELINE.json) before the network is bui
 import os
 import sys
 
-import numpy as np
 import torch
 import torch.distributed as dist
 

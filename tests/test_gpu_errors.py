@@ -2,7 +2,6 @@
 (LensError in the Python layer), never as a crash, and leave the library usable."""
 import ctypes as C
 
-import numpy as np
 import pytest
 import torch
 

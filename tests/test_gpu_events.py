@@ -7,7 +7,6 @@ import zipfile
 
 import numpy as np
 import pytest
-import torch
 
 from oracle import oracle as O
 
