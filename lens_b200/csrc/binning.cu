@@ -40,15 +40,17 @@ struct BinParams {
     int32_t *win_events;
 };
 
-// ROI crop + the reference's (y - shift, x - shift) indexing with python wrap-around.
-// `kept` counts in-ROI events (all bands see the same events, band 0 reports the count).
+// The reference's (y - shift, x - shift) indexing of a roi x roi tensor (collect_data.py:193-197) after
+// the crop offset: every index the reference accepts, i.e. [-roi, roi - 1] with python wrap-around for the
+// negative ones (x == roi lands in column roi - 1 for shift 1), is binned; anything else is cropped
+// (the reference would raise IndexError).  `kept` counts the binned events (all bands see the same
+// events, band 0 reports the count).
 __device__ __forceinline__ void bin_one(const BinParams &p, uint32_t *hist, int row0, int row1,
                                         int xe, int ye, int &kept)
 {
-    int xr = xe - p.roi_x0, yr = ye - p.roi_y0;
-    if ((unsigned)xr >= (unsigned)p.roi || (unsigned)yr >= (unsigned)p.roi) return;
+    int col = xe - p.roi_x0 - p.index_shift, row = ye - p.roi_y0 - p.index_shift;
+    if (col < -p.roi || col >= p.roi || row < -p.roi || row >= p.roi) return;
     ++kept;
-    int col = xr - p.index_shift, row = yr - p.index_shift;
     col += (col < 0) ? p.roi : 0;   // python negative index: -1 -> last
     row += (row < 0) ? p.roi : 0;
     if (row < row0 || row >= row1) return;

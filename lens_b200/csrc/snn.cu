@@ -31,6 +31,41 @@ namespace lens {
 // weights -> fixed point
 // --------------------------------------------------------------------------------
 // One CTA per output neuron n.  W [n_out][n_in] f32  ->  fx [n_in][n_out] i64, scale [n_out].
+// w = m * 2^q with q = emax - kFxBits (|m| < 2^46), then the trailing zero bits common to the whole
+// row are shifted out (q grows by the same amount, the products stay exact): fp32 weights carry 24
+// significant bits, so a row whose weights span s binary orders of magnitude needs only 24 + s bits,
+// i.e. fewer radix-256 digit planes on the tensor-core path (snn_tc.cu).
+__device__ __forceinline__ int64_t weight_to_fixed(float w, int q, bool &inexact)
+{
+    const uint32_t u = __float_as_uint(w);
+    const int ef = (u >> 23) & 255;
+    const uint32_t frac = u & 0x7fffffu;
+    int64_t m = 0;
+    inexact = false;
+    if (ef == 255) {
+        inexact = true;                                          // inf / nan -> 0, flagged
+    } else if (!(ef == 0 && frac == 0)) {
+        const int64_t mant = (ef == 0) ? (int64_t)frac : (int64_t)(frac | 0x800000u);
+        const int e_ulp = (ef == 0) ? -149 : ef - 150;           // w = mant * 2^e_ulp
+        const int sh = e_ulp - q;
+        if (sh >= 0) {
+            m = mant << sh;                                      // sh <= 22 by construction
+        } else {
+            const int r = -sh;
+            if (r > 26) { m = 0; inexact = true; }
+            else {
+                int64_t keep = mant >> r;
+                const int64_t rem = mant & ((1ll << r) - 1), half = 1ll << (r - 1);
+                if (rem > half || (rem == half && (keep & 1))) ++keep;   // RNE
+                if (rem) inexact = true;
+                m = keep;
+            }
+        }
+        if (u >> 31) m = -m;
+    }
+    return m;
+}
+
 __global__ void __launch_bounds__(256) weights_to_fixed_kernel(const float *__restrict__ W,
                                                                int n_out, int n_in,
                                                                int64_t *__restrict__ fx,
@@ -38,8 +73,9 @@ __global__ void __launch_bounds__(256) weights_to_fixed_kernel(const float *__re
                                                                int64_t *__restrict__ n_inexact)
 {
     __shared__ int s_emax;
+    __shared__ unsigned long long s_bits;
     const int n = blockIdx.x;
-    if (threadIdx.x == 0) s_emax = INT_MIN;
+    if (threadIdx.x == 0) { s_emax = INT_MIN; s_bits = 0ull; }
     __syncthreads();
     int emax = INT_MIN;
     for (int k = threadIdx.x; k < n_in; k += blockDim.x) {
@@ -56,34 +92,26 @@ __global__ void __launch_bounds__(256) weights_to_fixed_kernel(const float *__re
     emax = s_emax;
     int q = (emax == INT_MIN) ? 0 : emax - kFxBits;
     if (q < -126) q = -126;                                          // keep 2^q a normal float
-    if (threadIdx.x == 0) scale[n] = __uint_as_float((uint32_t)(q + 127) << 23);
+    // trailing zeros common to the row
+    unsigned long long bits = 0ull;
     int64_t bad = 0;
     for (int k = threadIdx.x; k < n_in; k += blockDim.x) {
-        uint32_t u = __float_as_uint(W[(size_t)n * n_in + k]);
-        int ef = (u >> 23) & 255;
-        uint32_t frac = u & 0x7fffffu;
-        int64_t m = 0;
-        if (ef == 255) {
-            ++bad;                                                   // inf / nan -> 0, flagged
-        } else if (!(ef == 0 && frac == 0)) {
-            int64_t mant = (ef == 0) ? (int64_t)frac : (int64_t)(frac | 0x800000u);
-            int e_ulp = (ef == 0) ? -149 : ef - 150;                 // w = mant * 2^e_ulp
-            int sh = e_ulp - q;
-            if (sh >= 0) {
-                m = mant << sh;                                      // sh <= 22 by construction
-            } else {
-                int r = -sh;
-                if (r > 26) { m = 0; ++bad; }
-                else {
-                    int64_t keep = mant >> r, rem = mant & ((1ll << r) - 1), half = 1ll << (r - 1);
-                    if (rem > half || (rem == half && (keep & 1))) ++keep;   // RNE
-                    if (rem) ++bad;
-                    m = keep;
-                }
-            }
-            if (u >> 31) m = -m;
-        }
-        fx[(size_t)k * n_out + n] = m;
+        bool inexact;
+        const int64_t m = weight_to_fixed(W[(size_t)n * n_in + k], q, inexact);
+        bits |= (unsigned long long)(m < 0 ? -m : m);
+        bad += inexact;
+    }
+    for (int o = 16; o > 0; o >>= 1) bits |= __shfl_xor_sync(0xffffffffu, bits, o);
+    if ((threadIdx.x & 31) == 0 && bits) atomicOr(&s_bits, bits);
+    __syncthreads();
+    bits = s_bits;
+    int tz = bits ? __ffsll((long long)bits) - 1 : 0;
+    if (q + tz > 127) tz = 127 - q;
+    if (threadIdx.x == 0) scale[n] = __uint_as_float((uint32_t)(q + tz + 127) << 23);
+    for (int k = threadIdx.x; k < n_in; k += blockDim.x) {
+        bool inexact;
+        const int64_t m = weight_to_fixed(W[(size_t)n * n_in + k], q, inexact);
+        fx[(size_t)k * n_out + n] = m >> tz;                         // exact: tz zero bits leave
     }
     for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
     if ((threadIdx.x & 31) == 0 && bad) atomicAdd((unsigned long long *)n_inexact, (unsigned long long)bad);
@@ -165,15 +193,16 @@ __global__ void __launch_bounds__(1024) feature_kernel(FeatureParams p)
     const int tid = threadIdx.x;
     const int warp = tid >> 5, nwarps = blockDim.x >> 5;
     const float thr = p.thr, vmin = p.vmin;
-    const int n_chunks = (p.steps + kChunk - 1) / kChunk;
+    const int n_chunks = n_chunks_of(p.steps, p.T);
     float v0 = (tid < I) ? p.v0[(size_t)b * I + tid] : 0.0f;
     float v1 = (tid < F) ? p.v1[(size_t)b * F + tid] : 0.0f;
     const float scale = (tid < F) ? p.Wf_scale[tid] : 0.0f;
     int64_t n_over = 0;
     float prob = 0.0f;
 
-    for (int t0 = 0; t0 < p.steps; t0 += kChunk) {
-        const int nc = min(kChunk, p.steps - t0);
+    for (int ch = 0; ch < n_chunks; ++ch) {
+        int t0, nc;
+        chunk_span(ch, p.steps, p.T, t0, nc);
         // ---- phase A: IAF#0 over the chunk (elementwise, no cross-thread dependency)
         if (tid < I) {
             for (int c = 0; c < nc; ++c) {
@@ -221,12 +250,12 @@ __global__ void __launch_bounds__(1024) feature_kernel(FeatureParams p)
         }
         __syncthreads();
         {   // the finished half tile leaves with 16-byte stores into its rows of the pair tile
-            uint4 *dst = reinterpret_cast<uint4 *>(p.S1 + ((size_t)(b >> 1) * n_chunks + t0 / kChunk) * s1_tile_bytes(p.Fp));
+            uint4 *dst = reinterpret_cast<uint4 *>(p.S1 + ((size_t)(b >> 1) * n_chunks + ch) * s1_tile_bytes(p.Fp));
             const uint4 *src = reinterpret_cast<const uint4 *>(tile);
             const int n16 = p.Fp / 16 * kChunk;
             const int sp = b & 1;
             for (int i = tid; i < n16; i += blockDim.x)
-                dst[(i / kChunk) * kTileRows + sp * kChunk + (i % kChunk)] = src[i];
+                dst[(i / kChunk) * kTileRows + s1_row(sp, i % kChunk)] = src[i];
         }
     }
     if (tid < I) p.v0[(size_t)b * I + tid] = v0;
@@ -336,7 +365,7 @@ __global__ void __launch_bounds__(1024, 1) feature_raster_kernel(RasterParams p)
     for (int i = threadIdx.x; i < I * F; i += blockDim.x) sW[i] = p.Wf_fx[i];
     const float scale = (f < F) ? p.Wf_scale[f] : 0.0f;
     const float vmin = p.vmin;
-    const int n_chunks = (p.steps + kChunk - 1) / kChunk;
+    const int n_chunks = n_chunks_of(p.steps, p.T);
     const uint32_t a_w = (uint32_t)__cvta_generic_to_shared(sW) + 8u * (uint32_t)(f < F ? f : 0);
     const uint32_t a_list = (uint32_t)__cvta_generic_to_shared(sList);
     const uint32_t a_cnt = (uint32_t)__cvta_generic_to_shared(sCnt);
@@ -350,8 +379,8 @@ __global__ void __launch_bounds__(1024, 1) feature_raster_kernel(RasterParams p)
         const bool live = b < p.nb;
         float v1 = (live && f < F) ? p.v1[(size_t)b * F + f] : 0.0f;
         for (int ch = 0; ch < n_chunks; ++ch) {
-            const int t0 = ch * kChunk;
-            const int nc = min(kChunk, p.steps - t0);
+            int t0, nc;
+            chunk_span(ch, p.steps, p.T, t0, nc);
             // ---- (A) active-input lists of this tile's steps (entries = weight-row offsets i * F)
             if (live) {
                 for (int c = slot_warp; c < nc; c += slot_warps) {
@@ -408,7 +437,7 @@ __global__ void __launch_bounds__(1024, 1) feature_raster_kernel(RasterParams p)
                 const int n16 = Fp / 16 * kChunk;
                 const int sp = b & 1;
                 for (int i = f; i < n16; i += slot_threads)
-                    dst[(i / kChunk) * kTileRows + sp * kChunk + (i % kChunk)] = src[i];
+                    dst[(i / kChunk) * kTileRows + s1_row(sp, i % kChunk)] = src[i];
             }
         }
         if (live && f < F) p.v1[(size_t)b * F + f] = v1;
@@ -487,18 +516,19 @@ __global__ void __launch_bounds__(kOutThreads) output_simt_kernel(OutputParams p
     const int64_t *wcol = p.Wo_fx + (live ? place : 0);
     float count = 0.0f;
     const int Q = p.steps / p.T;
-    const int n_chunks = (p.steps + kChunk - 1) / kChunk;
+    const int n_chunks = n_chunks_of(p.steps, p.T);
 
-    for (int t0 = 0; t0 < p.steps; t0 += kChunk) {
-        const int nc = min(kChunk, p.steps - t0);
+    for (int ch = 0; ch < n_chunks; ++ch) {
+        int t0, nc;
+        chunk_span(ch, p.steps, p.T, t0, nc);
         // stage this stream's rows of the pair tile with 16-byte loads
         {
-            const uint4 *src = reinterpret_cast<const uint4 *>(p.S1 + ((size_t)(b >> 1) * n_chunks + t0 / kChunk) * s1_tile_bytes(Fp));
+            const uint4 *src = reinterpret_cast<const uint4 *>(p.S1 + ((size_t)(b >> 1) * n_chunks + ch) * s1_tile_bytes(Fp));
             uint4 *dst = reinterpret_cast<uint4 *>(s1);
             const int n16 = Fp / 16 * kChunk;
             const int sp = b & 1;
             for (int i = tid; i < n16; i += kOutThreads)
-                dst[i] = __ldg(src + (i / kChunk) * kTileRows + sp * kChunk + (i % kChunk));
+                dst[i] = __ldg(src + (i / kChunk) * kTileRows + s1_row(sp, i % kChunk));
         }
         __syncthreads();
         for (int c = warp; c < nc; c += kOutThreads / 32) {
@@ -587,7 +617,7 @@ static int forward_common(SnnHandle *h, const uint8_t *pooled, const float *xin,
                           float *counts, float *spikes_out, uint8_t *hidden_steps,
                           uint8_t *out_steps, int mode, cudaStream_t st, int first_stream = 0)
 {
-    const size_t per_pair = (size_t)ceil_div(steps, kTileSteps) * s1_tile_bytes(h->Fp);
+    const size_t per_pair = (size_t)n_chunks_of(steps, h->T) * s1_tile_bytes(h->Fp);
     // streams are processed in groups (even size: a pair tile never straddles two groups)
     int group = (int)std::min<size_t>((size_t)B + (B & 1), 2 * std::max<size_t>((size_t)1, scratch_budget() / std::max<size_t>(per_pair, 1)));
     int rc = ensure_scratch(h, per_pair * (group / 2));

@@ -12,7 +12,7 @@
 // and scales by the row's 2^q: bit-identical to the event-driven kernel and to the CPU oracle.
 //
 // Mapping: M = 128 places (TMEM lanes), N = 64 columns = 32 consecutive timesteps of TWO streams
-// (columns 0..31 even stream, 32..63 odd stream), K = F padded to 32.  Time runs along the columns,
+// (column 2n + s = step n of stream s), K = F padded to 32.  Time runs along the columns,
 // so a thread owns one place and scans the columns of a stream serially with the membrane potential
 // and spike count in registers -- the recurrence never leaves the register file for a whole stream.
 // A CTA owns one place tile for the whole launch: its 6 digit planes (6 x 128 x Fp bytes, canonical
@@ -54,9 +54,9 @@ constexpr int kDrainGroups = 2;         // drain warpgroups; each owns kN / kDra
 constexpr int kNd = kN / kDrainGroups;  // (= the 32 steps of one stream)
 constexpr int kScanWarp0 = 4 + 4 * kDrainGroups;
 constexpr int kThreads = 128 * (2 + kDrainGroups);   // control + drain warpgroups + scan
-constexpr int kRegsControl = 56;        // setmaxnreg budgets: 128 * (56 + 2 * 152 + 152) = 512 * 128
-constexpr int kRegsDrain = 152;
-constexpr int kRegsScan = 152;
+constexpr int kRegsControl = 56;        // setmaxnreg budgets: 128 * (56 + 2 * 176 + 104) = 512 * 128
+constexpr int kRegsDrain = 176;
+constexpr int kRegsScan = 104;
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
     return (uint32_t)__cvta_generic_to_shared(p);
@@ -205,13 +205,15 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N)
 }
 
 struct Params {
-    const int8_t *planes;   // [P_tiles][kPlanes][Fp/16][128][16]
+    const int8_t *planes;   // [n_tiles][kPlanes][Fp/16][128][16]
+    const int *npl;         // [n_tiles] digit planes that are not all zero in the tile (5 or 6)
     const int8_t *S1;       // [pairs][chunks][Fp/16][64][16]
     const float *scale;     // [P]
     float *v2;              // [nb][P] (offset to the first stream of the launch)
     float *counts;          // [nb][Q][P]
     uint8_t *out_steps;     // nullable [nb][steps][P] (hidden layer: [nb][steps][P] hidden spikes)
     int P, Fp, T, steps, chunks, nb, n_pairs, n_tiles;
+    int pb_size, n_super;   // work = (pair block, place tile) super-items, tile fastest (see snn_tc_output)
     float thr, vmin;
     // hidden-layer variant (kHidden): the "places" are feature neurons and the result is their spike
     // raster, written as pair tiles for the output layer
@@ -219,7 +221,7 @@ struct Params {
     int out_Fp;
     int64_t *overflow;      // spike counts above LENS_MAX_SPIKE
 #ifdef LENS_TC_PROFILE
-    long long *prof;        // [gridDim.x][16] phase clocks of warps 1, 4 and 8 (profiling builds only)
+    long long *prof;        // [gridDim.x][24] phase clocks of warps 1, 4 and 12 (profiling builds only)
 #endif
 };
 
@@ -242,6 +244,13 @@ __device__ __forceinline__ void bulk_s2g(void *gmem_dst, const void *smem_src, u
                  : "memory");
 }
 
+__device__ __forceinline__ float fmax3(float a, float b, float c)
+{
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
 // One IAF#2 step on the exact contraction result.
 // kUnit: thr == 1 and v_min == -1 (the reference's fixed configuration, lens/run_model.py:151-156).
 // Then v / thr == v and s * thr == s exactly, (v > 0) * trunc(v / thr) is 0 below 1, 1 in [1, 2) and
@@ -261,8 +270,56 @@ __device__ __forceinline__ float iaf_out(float &v, float x, float thr, float vmi
     return iaf_step(v, x, thr, vmin);
 }
 
-// kKSteps = Fp / 32 as a compile-time constant (0 = generic runtime loop): with it the 6 x kKSteps
-// MMAs of a tile are straight-line code whose descriptors are constant offsets from two uniform bases.
+// Fast IAF#2 scan of one tile for BOTH streams of the pair (x[2n + s] = step n of stream s; v, csum:
+// .x = even stream, .y = odd stream), valid when thr == 1, v_min == -1 and no step fires twice.
+// Per step and stream the reference computes a = v + x; s = (a >= 1); v' = relu((a - s) + 1) - 1.
+// With c = 1 - s:  relu(fl(a + c)) == fl(max(a, -1) + c)  (both are 0 exactly when a < -1, because then
+// c = 1), so the chain per step is FADD2 -> {FSET, FMNMX} -> FADD2 -> FADD2 on packed f32x2 pairs.
+// csum accumulates c (steps WITHOUT a spike); amax = largest pre-spike potential of the tile, which
+// decides afterwards whether some step left the fast path's domain (a >= 2).
+template <bool kRagged>
+__device__ __forceinline__ void scan_tile_unit(const float (&x)[kN], int nvalid, float2 &v, float2 &csum, float &amax)
+{
+    const float2 m1 = make_float2(-1.0f, -1.0f);
+#pragma unroll
+    for (int n = 0; n < kTileSteps; ++n) {
+        if (!kRagged || n < nvalid) {
+            const float2 a = __fadd2_rn(v, make_float2(x[2 * n], x[2 * n + 1]));
+            const float2 c = make_float2(a.x >= 1.0f ? 0.0f : 1.0f, a.y >= 1.0f ? 0.0f : 1.0f);
+            const float2 lo = make_float2(fmaxf(a.x, -1.0f), fmaxf(a.y, -1.0f));
+            amax = fmax3(amax, a.x, a.y);
+            csum = __fadd2_rn(csum, c);
+            v = __fadd2_rn(__fadd2_rn(lo, c), m1);
+        }
+    }
+}
+
+// Fast IAF#1 scan (hidden layer): several spikes per step do occur (~3e-4 of neuron-steps), so the count
+// is computed exactly on the ALU in every step: for 0 <= m < 2^23, t = fl_rz(m + 2^23) is 2^23 + trunc(m),
+// its low byte is the spike count s itself, and (2^23 + 1) - t = 1 - s.  v - s is exact, so
+// relu(fl(a + (1 - s))) - 1 rounds like the reference's three operations.  The spike bytes go to the
+// staging tile rows 2n (even stream) and 2n + 1 (odd stream) of this lane's k-chunk.
+template <bool kRagged>
+__device__ __forceinline__ void scan_tile_hidden(const float (&x)[kN], int nvalid, float2 &v, float &amax, uint8_t *stage_out)
+{
+    const float2 m1 = make_float2(-1.0f, -1.0f), big = make_float2(8388608.0f, 8388608.0f);
+    const float2 big1 = make_float2(8388609.0f, 8388609.0f);
+#pragma unroll
+    for (int n = 0; n < kTileSteps; ++n) {
+        if (!kRagged || n < nvalid) {
+            const float2 a = __fadd2_rn(v, make_float2(x[2 * n], x[2 * n + 1]));
+            const float2 ta = __fadd2_rz(make_float2(fmaxf(a.x, 0.0f), fmaxf(a.y, 0.0f)), big);
+            amax = fmax3(amax, a.x, a.y);
+            const float2 r = __fadd2_rn(a, __ffma2_rn(ta, m1, big1));       // a + (1 - s)
+            v = __fadd2_rn(make_float2(fmaxf(r.x, 0.0f), fmaxf(r.y, 0.0f)), m1);
+            stage_out[(2 * n) * 16] = (uint8_t)__float_as_uint(ta.x);
+            stage_out[(2 * n + 1) * 16] = (uint8_t)__float_as_uint(ta.y);
+        }
+    }
+}
+
+// kKSteps = Fp / 32 as a compile-time constant (0 = generic runtime loop): with it the MMAs of a tile
+// are straight-line code whose descriptors are constant offsets from two uniform bases.
 // kHidden: feature layer (IAF#1) instead of output layer (IAF#2): spikes leave as pair tiles, no counts.
 template <bool kUnitThr, bool kDebug, int kKSteps, bool kHidden>
 __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
@@ -286,11 +343,10 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
     uint8_t *sOut = reinterpret_cast<uint8_t *>(bars) + 256;  // [2][8][64][16] spike staging (kHidden only)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // Work items = (place tile, stream pair) in tile-major order; persistent CTAs take contiguous,
-    // equally sized ranges, so a CTA changes its place tile (and reloads the digit planes) at most a
-    // few times and every SM gets the same amount of work whatever P is.
-    const long long n_items = (long long)p.n_tiles * p.n_pairs;
-    const int item0 = (int)(n_items * blockIdx.x / gridDim.x), item1 = (int)(n_items * (blockIdx.x + 1) / gridDim.x);
+    // Work = super-items (pair block, place tile), tile fastest, dealt round-robin to the persistent CTAs:
+    // the CTAs running at the same time work on the same few pair blocks with different place tiles, so a
+    // hidden-spike tile is fetched from HBM once and then served from L2 to the other place tiles; a CTA
+    // keeps its digit planes for the pb_size stream pairs of the block.
 
     if (threadIdx.x == 0) {
         mbar_init(a_full, 1);
@@ -318,32 +374,34 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
     if (warp == 0) {
         // ===================== TMA producer (warp-uniform, one elected lane issues) ==============
         uint32_t it = 0;
-        int cur_tile = -1;
-        for (int item = item0; item < item1; ++item) {
-            const int tile = item / p.n_pairs, pr = item - tile * p.n_pairs;
-            if (tile != cur_tile) {
-                // new place tile: every MMA that reads the old planes must have retired
-                if (cur_tile >= 0)
-                    for (uint32_t j = it > (uint32_t)kStages ? it - kStages : 0; j < it; ++j)
-                        mbar_wait(b_empty + j % kStages, (j / kStages) & 1);
-                if (elect_one()) {
-                    mbar_expect_tx(a_full, kPlanes * plane_bytes);
-                    const int8_t *src = p.planes + (size_t)tile * kPlanes * plane_bytes;
-                    for (int j = 0; j < kPlanes; ++j)
-                        bulk_g2s(sA + j * plane_bytes, src + (size_t)j * plane_bytes, plane_bytes, a_full);
-                }
-                __syncwarp();
-                cur_tile = tile;
+        bool first = true;
+        for (int u = blockIdx.x; u < p.n_super; u += gridDim.x) {
+            const int pb = u / p.n_tiles, tile = u - pb * p.n_tiles;
+            const int pr0 = pb * p.pb_size, pr1 = min(pr0 + p.pb_size, p.n_pairs);
+            const uint32_t a_bytes = (uint32_t)__ldg(p.npl + tile) * plane_bytes;
+            // new place tile: every MMA that reads the old planes must have retired
+            if (!first)
+                for (uint32_t j = it > (uint32_t)kStages ? it - kStages : 0; j < it; ++j)
+                    mbar_wait(b_empty + j % kStages, (j / kStages) & 1);
+            first = false;
+            if (elect_one()) {
+                mbar_expect_tx(a_full, a_bytes);
+                const int8_t *src = p.planes + (size_t)tile * kPlanes * plane_bytes;
+                for (uint32_t o = 0; o < a_bytes; o += plane_bytes)
+                    bulk_g2s(sA + o, src + o, plane_bytes, a_full);
             }
-            const int8_t *sb = p.S1 + (size_t)pr * p.chunks * tile_bytes;
-            for (int c = 0; c < p.chunks; ++c, ++it) {
-                const uint32_t stage = it % kStages, phase = (it / kStages) & 1;
-                mbar_wait(b_empty + stage, phase ^ 1);
-                if (elect_one()) {
-                    mbar_expect_tx(b_full + stage, tile_bytes);
-                    bulk_g2s(sB + stage * tile_bytes, sb + (size_t)c * tile_bytes, tile_bytes, b_full + stage);
+            __syncwarp();
+            for (int pr = pr0; pr < pr1; ++pr) {
+                const int8_t *sb = p.S1 + (size_t)pr * p.chunks * tile_bytes;
+                for (int c = 0; c < p.chunks; ++c, ++it) {
+                    const uint32_t stage = it % kStages, phase = (it / kStages) & 1;
+                    mbar_wait(b_empty + stage, phase ^ 1);
+                    if (elect_one()) {
+                        mbar_expect_tx(b_full + stage, tile_bytes);
+                        bulk_g2s(sB + stage * tile_bytes, sb + (size_t)c * tile_bytes, tile_bytes, b_full + stage);
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         }
     } else {
@@ -363,13 +421,14 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
         const uint64_t da_a = da0 + (uint32_t)(2 * g) * a_plane, da_b = da_a + a_plane;
         const uint32_t d_a = tmem_base + (2 * g) * kN, d_b = d_a + kN;
         uint32_t it = 0, a_phase = 0;
-        int cur_tile = -1;
         PROF_DECL;
-        for (int item = item0; item < item1; ++item) {
-            const int tile = item / p.n_pairs;
-            if (tile != cur_tile) { mbar_wait(a_full, a_phase); a_phase ^= 1; cur_tile = tile; }   // planes landed
+        for (int u = blockIdx.x; u < p.n_super; u += gridDim.x) {
+            const int pb = u / p.n_tiles, tile = u - pb * p.n_tiles;
+            const int n_it = (min(pb * p.pb_size + p.pb_size, p.n_pairs) - pb * p.pb_size) * p.chunks;
+            const bool both = 2 * g + 1 < __ldg(p.npl + tile);    // the pair's upper plane is not all zero
+            mbar_wait(a_full, a_phase); a_phase ^= 1;               // planes landed
             PROF(0);
-            for (int c = 0; c < p.chunks; ++c, ++it) {
+            for (int i = 0; i < n_it; ++i, ++it) {
                 const uint32_t stage = it % kStages, phase = (it / kStages) & 1;
                 GANTT(0 + 5 * g);
                 mbar_wait(b_full + stage, phase);           // spikes landed
@@ -384,16 +443,27 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
                 PROF(2);
                 GANTT(2 + 5 * g);
                 if (elect_one()) {
-                    if (kKSteps > 0) {
+                    if (both) {
+                        if (kKSteps > 0) {
 #pragma unroll
-                        for (int ks = 0; ks < kKSteps; ++ks) {
-                            mma_i8(d_a, da_a + ks * a_kstep, db_s + ks * b_kstep, idesc, ks > 0 ? 1u : 0u);
-                            mma_i8(d_b, da_b + ks * a_kstep, db_s + ks * b_kstep, idesc, ks > 0 ? 1u : 0u);
+                            for (int ks = 0; ks < kKSteps; ++ks) {
+                                mma_i8(d_a, da_a + ks * a_kstep, db_s + ks * b_kstep, idesc, ks > 0 ? 1u : 0u);
+                                mma_i8(d_b, da_b + ks * a_kstep, db_s + ks * b_kstep, idesc, ks > 0 ? 1u : 0u);
+                            }
+                        } else {
+                            for (int ks = 0; ks < ksteps; ++ks) {
+                                mma_i8(d_a, da_a + ks * a_kstep, db_s + ks * b_kstep, idesc, ks > 0 ? 1u : 0u);
+                                mma_i8(d_b, da_b + ks * a_kstep, db_s + ks * b_kstep, idesc, ks > 0 ? 1u : 0u);
+                            }
                         }
                     } else {
-                        for (int ks = 0; ks < ksteps; ++ks) {
-                            mma_i8(d_a, da_a + ks * a_kstep, db_s + ks * b_kstep, idesc, ks > 0 ? 1u : 0u);
-                            mma_i8(d_b, da_b + ks * a_kstep, db_s + ks * b_kstep, idesc, ks > 0 ? 1u : 0u);
+                        if (kKSteps > 0) {
+#pragma unroll
+                            for (int ks = 0; ks < kKSteps; ++ks)
+                                mma_i8(d_a, da_a + ks * a_kstep, db_s + ks * b_kstep, idesc, ks > 0 ? 1u : 0u);
+                        } else {
+                            for (int ks = 0; ks < ksteps; ++ks)
+                                mma_i8(d_a, da_a + ks * a_kstep, db_s + ks * b_kstep, idesc, ks > 0 ? 1u : 0u);
                         }
                     }
                     GANTT(3 + 5 * g);
@@ -410,35 +480,47 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
     }
     } else if (warp < kScanWarp0) {
         // ===================== drain warpgroups: TMEM accumulators -> exact fp32 contraction results =========
-        // warpgroup dw owns columns [dw * kNd, (dw + 1) * kNd) of every plane (the 32 steps of stream dw)
+        // warpgroup dw owns columns [dw * kNd, (dw + 1) * kNd) of every plane (16 steps of both streams)
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsDrain));
         const int quarter = warp & 3;                          // TMEM lanes this warp may touch
         const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((warp - 4) >> 2) * kNd;
         int it = 0;
         uint32_t probe0 = 0;
+        bool preloaded = false;     // the coming tile's first loads (pair 0, columns 0..15) are already in flight
         PROF_DECL;
-        for (int item = item0; item < item1; ++item) {
-        const int place = (item / p.n_pairs) * kM + quarter * 32 + lane;
+        for (int u = blockIdx.x; u < p.n_super; u += gridDim.x) {
+        const int pb = u / p.n_tiles, tile = u - pb * p.n_tiles;
+        const int n_it = (min(pb * p.pb_size + p.pb_size, p.n_pairs) - pb * p.pb_size) * p.chunks;
+        const bool top2 = __ldg(p.npl + tile) > 5;             // plane 5 present
+        const int place = tile * kM + quarter * 32 + lane;
         const float scale = place < p.P ? p.scale[place] : 0.0f;
-        for (int c = 0; c < p.chunks; ++c, ++it) {
+        for (int i = 0; i < n_it; ++i, ++it) {
             // X = sum_j P_j 256^j as (xh:xl) for the kNd columns of this lane.  The (pair, 16-column) loads
             // are double-buffered in registers: the tcgen05.ld of step s + 1 is in flight while step s is
-            // folded into X, so only the first load's latency is exposed.
+            // folded into X, and the first load of the NEXT tile is issued before the last fold and the
+            // int64 -> fp32 conversions (XU pipe), which hide its latency.
             int32_t xl[kNd], xh[kNd];
             int32_t buf[2][32];
             uint32_t probe = 0;
+            const uint32_t xb = it & 1;
             constexpr int kH = kNd / 16, kSteps = 3 * kH;
+            static_assert(kH == 2, "the drain schedule below assumes two 16-column halves per warpgroup");
             PROF(1);
             GANTT(16);
-            mbar_wait_probed(probe0, acc_full + 0, it & 1);
-            tc_fence_after();
+            if (!preloaded) {
+                mbar_wait_probed(probe0, acc_full + 0, it & 1);
+                tc_fence_after();
+            }
             // in steady state the MMA warps are a tile ahead: poll the other two pairs now, so that the
             // polls' latency hides behind the first pair's loads and folding
             const uint32_t probe1 = mbar_probe(acc_full + 1, it & 1), probe2 = mbar_probe(acc_full + 2, it & 1);
             PROF(0);
             GANTT(17);
-            tmem_ld16(tlane + 0 * kN, reinterpret_cast<int32_t(&)[16]>(buf[0][0]));
-            tmem_ld16(tlane + 1 * kN, reinterpret_cast<int32_t(&)[16]>(buf[0][16]));
+            if (!preloaded) {
+                tmem_ld16(tlane + 0 * kN, reinterpret_cast<int32_t(&)[16]>(buf[0][0]));
+                tmem_ld16(tlane + 1 * kN, reinterpret_cast<int32_t(&)[16]>(buf[0][16]));
+            }
+            preloaded = false;
 #pragma unroll
             for (int s = 0; s < kSteps; ++s) {
                 const int g = s / kH, h = s % kH;
@@ -465,34 +547,50 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
                         GANTT(17 + 2 * g2);
                     }
                     tmem_ld16(tlane + (2 * g2) * kN + h2 * 16, reinterpret_cast<int32_t(&)[16]>(buf[(s + 1) & 1][0]));
-                    tmem_ld16(tlane + (2 * g2 + 1) * kN + h2 * 16, reinterpret_cast<int32_t(&)[16]>(buf[(s + 1) & 1][16]));
-                    if (s + 1 == 2 * kH) probe = mbar_probe(x_empty + (it & 1), ((it >> 1) & 1) ^ 1);
+                    if (g2 < 2 || top2)
+                        tmem_ld16(tlane + (2 * g2 + 1) * kN + h2 * 16, reinterpret_cast<int32_t(&)[16]>(buf[(s + 1) & 1][16]));
+                    if (s + 1 == 2 * kH) {
+                        probe = mbar_probe(x_empty + (it & 1), ((it >> 1) & 1) ^ 1);
+                        probe0 = mbar_probe(acc_full + 0, (it + 1) & 1);        // next tile's first pair
+                    }
+                } else {
+                    // last step: start the next tile's first loads (pair 0, columns 0..15) into the free buffer
+                    const bool more = (i + 1 < n_it) || (u + (int)gridDim.x < p.n_super);
+                    if (more && (probe0 || mbar_probe(acc_full + 0, (it + 1) & 1))) {
+                        tc_fence_after();
+                        tmem_ld16(tlane + 0 * kN, reinterpret_cast<int32_t(&)[16]>(buf[0][0]));
+                        tmem_ld16(tlane + 1 * kN, reinterpret_cast<int32_t(&)[16]>(buf[0][16]));
+                        preloaded = true;
+                    }
                 }
+                if (g == 2 && !top2) {
 #pragma unroll
-                for (int n = 0; n < 16; ++n) {
-                    const int m = h * 16 + n;
-                    const int32_t qq = buf[s & 1][16 + n] * 256 + buf[s & 1][n];          // |qq| < 2^30
-                    if (g == 0) {
-                        xl[m] = qq;
-                    } else if (g == 1) {
-                        const int64_t t = (int64_t)xl[m] + ((int64_t)qq << 16);
-                        xl[m] = (int32_t)(uint32_t)t;
-                        xh[m] = (int32_t)(t >> 32);
-                    } else {
-                        xh[m] += qq;
+                    for (int n = 0; n < 16; ++n) xh[h * 16 + n] += buf[s & 1][n];              // plane 4 alone
+                } else {
+#pragma unroll
+                    for (int n = 0; n < 16; ++n) {
+                        const int m = h * 16 + n;
+                        const int32_t qq = buf[s & 1][16 + n] * 256 + buf[s & 1][n];          // |qq| < 2^30
+                        if (g == 0) {
+                            xl[m] = qq;
+                        } else if (g == 1) {
+                            const int64_t t = (int64_t)xl[m] + ((int64_t)qq << 16);
+                            xl[m] = (int32_t)(uint32_t)t;
+                            xh[m] = (int32_t)(t >> 32);
+                        } else {
+                            xh[m] += qq;
+                        }
                     }
                 }
             }
             // one rounding to fp32 (cvt.rn.f32.s64), exact power-of-two scale, hand over through TMEM
-            const uint32_t xb = it & 1;
             PROF(1);
             mbar_wait_probed(probe, x_empty + xb, ((it >> 1) & 1) ^ 1);
             tc_fence_after();
             PROF(2);
             GANTT(23);
-            probe0 = mbar_probe(acc_full + 0, (it + 1) & 1);        // next tile's first pair
 #pragma unroll
-            for (int h = 0; h < kNd / 16; ++h) {
+            for (int h = 0; h < kH; ++h) {
                 float xf[16];
 #pragma unroll
                 for (int n = 0; n < 16; ++n) {
@@ -511,25 +609,28 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
         }
         if (warp == 4) PROF_FLUSH(6);
     } else {
-        // ===================== scan warpgroup: IAF#2 recurrence of both streams, spike counts ================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsScan));
+        // ===================== scan warpgroup: IAF recurrence of both streams, spike counts ================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsScan));
         const int quarter = warp & 3;
         const float thr = p.thr, vmin = p.vmin;
         const int Q = p.steps / p.T;
+        const int cpq = chunks_per_query(p.T);
         const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
         long long n_over = 0;
         int it = 0;
         PROF_DECL;
-        for (int item = item0; item < item1; ++item) {
-            const int tile = item / p.n_pairs, pr = item - tile * p.n_pairs;
-            const int place = tile * kM + quarter * 32 + lane;
-            const bool live_place = place < p.P;
+        for (int u = blockIdx.x; u < p.n_super; u += gridDim.x) {
+        const int pb = u / p.n_tiles, tile = u - pb * p.n_tiles;
+        const int pr0 = pb * p.pb_size, pr1 = min(pr0 + p.pb_size, p.n_pairs);
+        const int place = tile * kM + quarter * 32 + lane;
+        const bool live_place = place < p.P;
+        for (int pr = pr0; pr < pr1; ++pr) {
             const int b0 = 2 * pr, b1 = 2 * pr + 1;
             const bool live0 = live_place && b0 < p.nb, live1 = live_place && b1 < p.nb;
-            float v0 = live0 ? p.v2[(size_t)b0 * p.P + place] : 0.0f;
-            float v1 = live1 ? p.v2[(size_t)b1 * p.P + place] : 0.0f;
-            float count0 = 0.0f, count1 = 0.0f;
-            int t_in_q = 0, q = 0;                               // both streams share the timeline
+            float2 v = make_float2(live0 ? p.v2[(size_t)b0 * p.P + place] : 0.0f,
+                                   live1 ? p.v2[(size_t)b1 * p.P + place] : 0.0f);
+            float2 count = make_float2(0.0f, 0.0f);
+            int cq = 0, q = 0;                                   // chunk within the query, query index
             for (int c = 0; c < p.chunks; ++c, ++it) {
                 const uint32_t xb = it & 1;
                 float x[kN];
@@ -552,8 +653,13 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
                 if (lane == 0) mbar_arrive(x_empty + xb);
                 PROF(2);
                 GANTT(34);
-                if (!kHidden && !live0 && !live1) continue;
-                // hidden layer: this tile's spike bytes are staged in shared memory [kc][row = stream*32+n][16]
+                // this chunk: steps [t_base, t_base + nvalid) of query q (chunks never straddle a query)
+                const int t_base = q * p.T + cq * kTileSteps;
+                const int nvalid = min(kTileSteps, min(p.T - cq * kTileSteps, p.steps - t_base));
+                const bool q_done = (cq + 1) * kTileSteps >= p.T;
+                if (++cq == cpq) { cq = 0; }
+                if (!kHidden && !live0 && !live1) { if (q_done) ++q; continue; }
+                // hidden layer: this tile's spike bytes are staged in shared memory [kc][row = 2n + stream][16]
                 uint8_t *stage_out = sOut + (it & 1) * 8192 + (quarter * 2 + (lane >> 4)) * 1024 + (lane & 15);
                 if (kHidden) {
                     // every scan warp ships its own 32 neurons (two 1 KB k-chunks), so the staging buffers need
@@ -562,119 +668,67 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
                     __syncwarp();
                 }
 
-                const int t_base = c * kTileSteps;
-                const int nvalid = min(kTileSteps, p.steps - t_base);
-                bool redo0 = live0, redo1 = live1;
-                if (kUnitThr && !kDebug && nvalid == kTileSteps && (kHidden || p.T >= kTileSteps)) {
-                    // Fast path: at most one spike per step is assumed (checked; a stream whose tile turns out
-                    // to hold a multi-spike step is redone below), which keeps each loop-carried chain at
-                    // FADD -> FSET -> FADD -> FMNMX -> FADD; the two streams give two independent chains.
-                    // A query may end inside the tile: the spikes of steps <= nb go to the ending query.
-                    const int nb = p.T - 1 - t_in_q;             // tile-local index of the query's last step
-                    const float s0 = v0, s1 = v1;
-                    float all0 = 0.0f, head0 = 0.0f, all1 = 0.0f, head1 = 0.0f;
-                    // the largest pre-spike potential of the tile decides afterwards whether a step overflowed
-                    // the fast path (one FMNMX per step instead of a compare and a predicate OR)
-                    float amax0 = -1.0f, amax1 = -1.0f;
-                    bool multi0, multi1;
+                bool redo = true;
+                if (kUnitThr && !kDebug) {
+                    // Fast path: both streams as packed f32x2 chains (see scan_tile_*); a tile in which some
+                    // step leaves the fast path's domain is redone step by step below.
+                    const float2 saved = v;
+                    float amax = -1.0f;
                     if (kHidden) {
-                        // Hidden layer: several spikes per step do occur (~3e-4 of neuron-steps), so the count is
-                        // computed exactly on the ALU in every step: for 0 <= m < 2^23, t = fl_rz(m + 2^23) is
-                        // 2^23 + trunc(m), its low byte is the spike count s itself, and (2^23 + 1) - t = 1 - s.
-#pragma unroll
-                        for (int n = 0; n < kTileSteps; ++n) {
-                            const float a = __fadd_rn(v0, x[n]), b = __fadd_rn(v1, x[kTileSteps + n]);
-                            const float ta = __fadd_rz(fmaxf(a, 0.0f), 8388608.0f), tb = __fadd_rz(fmaxf(b, 0.0f), 8388608.0f);
-                            amax0 = fmaxf(amax0, a); amax1 = fmaxf(amax1, b);
-                            // v - s is exact, so relu(v - s + 1) - 1 rounds like the reference's three operations
-                            v0 = __fadd_rn(fmaxf(__fadd_rn(a, __fsub_rn(8388609.0f, ta)), 0.0f), -1.0f);
-                            v1 = __fadd_rn(fmaxf(__fadd_rn(b, __fsub_rn(8388609.0f, tb)), 0.0f), -1.0f);
-                            stage_out[n * 16] = (uint8_t)__float_as_uint(ta);
-                            stage_out[512 + n * 16] = (uint8_t)__float_as_uint(tb);
-                        }
-                        multi0 = amax0 >= 128.0f; multi1 = amax1 >= 128.0f;   // beyond LENS_MAX_SPIKE: generic path
+                        if (nvalid == kTileSteps) scan_tile_hidden<false>(x, nvalid, v, amax, stage_out);
+                        else scan_tile_hidden<true>(x, nvalid, v, amax, stage_out);
+                        redo = amax >= 128.0f;                       // beyond LENS_MAX_SPIKE: generic path
                     } else {
-                        // spikes are collected as one bit per step; the counts are popcounts of the masks
-                        uint32_t m0 = 0u, m1 = 0u;
-#pragma unroll
-                        for (int n = 0; n < kTileSteps; ++n) {
-                            const float a = __fadd_rn(v0, x[n]), b = __fadd_rn(v1, x[kTileSteps + n]);
-                            const float ca = (a >= 1.0f) ? 0.0f : 1.0f, cb = (b >= 1.0f) ? 0.0f : 1.0f;   // 1 - s
-                            if (a >= 1.0f) m0 |= 1u << n;
-                            if (b >= 1.0f) m1 |= 1u << n;
-                            amax0 = fmaxf(amax0, a); amax1 = fmaxf(amax1, b);
-                            v0 = __fadd_rn(fmaxf(__fadd_rn(a, ca), 0.0f), -1.0f);
-                            v1 = __fadd_rn(fmaxf(__fadd_rn(b, cb), 0.0f), -1.0f);
+                        float2 csum = make_float2(0.0f, 0.0f);
+                        if (nvalid == kTileSteps) scan_tile_unit<false>(x, nvalid, v, csum, amax);
+                        else scan_tile_unit<true>(x, nvalid, v, csum, amax);
+                        redo = amax >= 2.0f;                         // several spikes in one step
+                        if (!redo) {
+                            count.x += (float)nvalid - csum.x;       // small integers: exact
+                            count.y += (float)nvalid - csum.y;
                         }
-                        multi0 = amax0 >= 2.0f; multi1 = amax1 >= 2.0f;
-                        const uint32_t head_mask = nb >= kTileSteps - 1 ? 0xffffffffu : ((2u << nb) - 1u);
-                        all0 = (float)__popc(m0); head0 = (float)__popc(m0 & head_mask);
-                        all1 = (float)__popc(m1); head1 = (float)__popc(m1 & head_mask);
                     }
-                    const bool boundary = nb < kTileSteps;
-                    if (kHidden) {
-                        redo0 = multi0; redo1 = multi1;
-                        if (multi0) v0 = s0;
-                        if (multi1) v1 = s1;
-                    } else {
-                    if (live0 && !multi0) {
-                        redo0 = false;
-                        if (boundary) { p.counts[((size_t)b0 * Q + q) * p.P + place] = count0 + head0; count0 = all0 - head0; }
-                        else count0 += all0;
-                    } else v0 = s0;
-                    if (live1 && !multi1) {
-                        redo1 = false;
-                        if (boundary) { p.counts[((size_t)b1 * Q + q) * p.P + place] = count1 + head1; count1 = all1 - head1; }
-                        else count1 += all1;
-                    } else v1 = s1;
-                    }
-                } else if (kHidden) {
-                    redo0 = redo1 = true;
+                    if (redo) v = saved;
                 }
-                // generic: multi-spike steps, ragged last tile, debug output, tiny T, other thresholds
-                int tq0 = t_in_q, q0 = q;
-                if (redo0) {
+                // generic: multi-spike steps, debug output, other thresholds
+                if (redo) {
 #pragma unroll
-                    for (int n = 0; n < kTileSteps; ++n) {
-                        if (n < nvalid) {
-                            float s = iaf_out<kUnitThr>(v0, x[n], thr, vmin);
-                            if (kHidden) {
-                                if (s > (float)LENS_MAX_SPIKE) { s = (float)LENS_MAX_SPIKE; if (live0) ++n_over; }
-                                stage_out[n * 16] = (uint8_t)s;
-                                if (kDebug && live0) p.out_steps[((size_t)b0 * p.steps + t_base + n) * p.P + place] = (uint8_t)s;
-                                continue;
+                    for (int sp = 0; sp < 2; ++sp) {
+                        const bool live = sp ? live1 : live0;
+                        const int b = sp ? b1 : b0;
+                        float vv = sp ? v.y : v.x, cnt = 0.0f;
+                        if (kHidden || live) {
+#pragma unroll
+                            for (int n = 0; n < kTileSteps; ++n) {
+                                if (n < nvalid) {
+                                    float s = iaf_out<kUnitThr>(vv, x[2 * n + sp], thr, vmin);
+                                    if (kHidden) {
+                                        if (s > (float)LENS_MAX_SPIKE) { s = (float)LENS_MAX_SPIKE; if (live) ++n_over; }
+                                        stage_out[(2 * n + sp) * 16] = (uint8_t)s;
+                                        if (kDebug && live) p.out_steps[((size_t)b * p.steps + t_base + n) * p.P + place] = (uint8_t)s;
+                                    } else {
+                                        if (kDebug) p.out_steps[((size_t)b * p.steps + t_base + n) * p.P + place] = (uint8_t)fminf(s, 255.0f);
+                                        cnt += s;
+                                    }
+                                }
                             }
-                            if (kDebug) p.out_steps[((size_t)b0 * p.steps + t_base + n) * p.P + place] = (uint8_t)fminf(s, 255.0f);
-                            count0 += s;
-                            if (++tq0 == p.T) { p.counts[((size_t)b0 * Q + q0) * p.P + place] = count0; count0 = 0.0f; tq0 = 0; ++q0; }
                         }
+                        if (sp) { v.y = vv; count.y += cnt; } else { v.x = vv; count.x += cnt; }
                     }
                 }
-                if (redo1) {
-                    int tq1 = t_in_q, q1 = q;
-#pragma unroll
-                    for (int n = 0; n < kTileSteps; ++n) {
-                        if (n < nvalid) {
-                            float s = iaf_out<kUnitThr>(v1, x[kTileSteps + n], thr, vmin);
-                            if (kHidden) {
-                                if (s > (float)LENS_MAX_SPIKE) { s = (float)LENS_MAX_SPIKE; if (live1) ++n_over; }
-                                stage_out[512 + n * 16] = (uint8_t)s;
-                                if (kDebug && live1) p.out_steps[((size_t)b1 * p.steps + t_base + n) * p.P + place] = (uint8_t)s;
-                                continue;
-                            }
-                            if (kDebug) p.out_steps[((size_t)b1 * p.steps + t_base + n) * p.P + place] = (uint8_t)fminf(s, 255.0f);
-                            count1 += s;
-                            if (++tq1 == p.T) { p.counts[((size_t)b1 * Q + q1) * p.P + place] = count1; count1 = 0.0f; tq1 = 0; ++q1; }
-                        }
+                if (!kHidden && q_done) {
+                    // last chunk of query q: its similarity row entries (lens/run_model.py:239)
+                    if (q < Q) {
+                        if (live0) p.counts[((size_t)b0 * Q + q) * p.P + place] = count.x;
+                        if (live1) p.counts[((size_t)b1 * Q + q) * p.P + place] = count.y;
                     }
+                    count = make_float2(0.0f, 0.0f);
                 }
+                if (q_done) ++q;
                 PROF(3);
                 GANTT(35);
-                // advance the shared timeline by the tile's valid steps
-                t_in_q += nvalid;
-                while (t_in_q >= p.T) { t_in_q -= p.T; ++q; }
                 if (kHidden) {
-                    for (int n = nvalid; n < kTileSteps; ++n) { stage_out[n * 16] = 0; stage_out[512 + n * 16] = 0; }
+                    for (int n = nvalid; n < kTileSteps; ++n) { stage_out[(2 * n) * 16] = 0; stage_out[(2 * n + 1) * 16] = 0; }
                     // generic-proxy writes -> async proxy, then one lane ships the warp's two k-chunks of the
                     // tile (contiguous in the pair-tile layout) with one bulk store
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -688,8 +742,9 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
                     }
                 }
             }
-            if (live0) p.v2[(size_t)b0 * p.P + place] = v0;
-            if (live1) p.v2[(size_t)b1 * p.P + place] = v1;
+            if (live0) p.v2[(size_t)b0 * p.P + place] = v.x;
+            if (live1) p.v2[(size_t)b1 * p.P + place] = v.y;
+        }
         }
         if (warp == kScanWarp0) PROF_FLUSH(12);
         if (kHidden) {
@@ -707,13 +762,18 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
 
 // Wo_fx [F][P] int64 fixed point -> balanced radix-256 digit planes in the canonical UMMA layout.
 // grid = (P_tiles, Fp/16); block = 128 (one thread per row of the tile).
+// npl[tile] (initialised to the minimum the kernel supports, 5) is raised to the number of planes that are
+// not entirely zero in the tile: the MMAs, the operand loads and the accumulator drains of the missing
+// top plane are skipped (after weights_to_fixed_kernel removed the row's common trailing zeros, rows whose
+// weights span <= 15 binary orders of magnitude fit 5 planes).
 __global__ void __launch_bounds__(128) planes_kernel(const int64_t *__restrict__ Wo_fx, int F, int P, int Fp,
-                                                     int8_t *__restrict__ planes)
+                                                     int8_t *__restrict__ planes, int *__restrict__ npl)
 {
     const int tile = blockIdx.x, kc = blockIdx.y, row = threadIdx.x;
     const int place = tile * kM + row;
     const size_t plane_bytes = (size_t)kM * Fp;
     int8_t dig[kPlanes][16];
+    int top = 0;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         const int k = kc * 16 + i;
@@ -722,14 +782,49 @@ __global__ void __launch_bounds__(128) planes_kernel(const int64_t *__restrict__
         for (int j = 0; j < kPlanes; ++j) {
             const int64_t d = ((m + 128) & 255) - 128;      // balanced digit in [-128, 127]
             dig[j][i] = (int8_t)d;
+            if (d != 0) top = max(top, j + 1);
             m = (m - d) >> 8;                                // exact: m - d is a multiple of 256
         }
     }
+    top = __reduce_max_sync(0xffffffffu, top);
+    if ((threadIdx.x & 31) == 0 && top > 5) atomicMax(npl + tile, top);
 #pragma unroll
     for (int j = 0; j < kPlanes; ++j) {
         int8_t *dst = planes + ((size_t)tile * kPlanes + j) * plane_bytes + ((size_t)kc * kM + row) * 16;
         *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(dig[j]);
     }
+}
+
+__global__ void fill_int_kernel(int *dst, int n, int value)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = value;
+}
+
+// Work decomposition of a launch: super-items = (block of pb_size stream pairs, place tile), tile fastest,
+// dealt round-robin to `grid` persistent CTAs.  pb_size balances three things: the makespan (rounds x
+// pb_size pair-items, every pair-item costs the same), the digit-plane reloads (once per super-item), and
+// the L2 footprint of the pair blocks in flight (their spike tiles should be fetched from HBM only once).
+static void schedule(Params &p, int sms, size_t pair_bytes, unsigned &grid)
+{
+    long long cost[17], best_cost = -1;
+    for (int m = 1; m <= 16; ++m) {
+        const long long n_super = (long long)ceil_div(p.n_pairs, m) * p.n_tiles;
+        cost[m] = ceil_div64(n_super, std::min<long long>(sms, n_super)) * m;
+        if (best_cost < 0 || cost[m] < best_cost) best_cost = cost[m];
+    }
+    int best_m = 0, smallest = 0;
+    for (int m = 1; m <= 16; ++m) {
+        if (cost[m] * 200 > best_cost * 201) continue;               // within 0.5 % of the best makespan
+        if (!smallest) smallest = m;
+        const long long n_super = (long long)ceil_div(p.n_pairs, m) * p.n_tiles;
+        const double window = (double)ceil_div64(std::min<long long>(sms, n_super), p.n_tiles) * m * (double)pair_bytes;
+        if (window <= 64.0 * 1024 * 1024) best_m = m;                // largest block whose window fits L2
+    }
+    if (!best_m) best_m = smallest;
+    p.pb_size = best_m;
+    p.n_super = ceil_div(p.n_pairs, best_m) * p.n_tiles;
+    grid = (unsigned)std::min<long long>(sms, p.n_super);
 }
 
 static size_t smem_bytes(int Fp, bool hidden = false)
@@ -747,6 +842,7 @@ __global__ void __launch_bounds__(256) raster_tiles_kernel(const uint8_t *__rest
                                                            int steps, int chunks, int nb, int n_pairs,
                                                            int8_t *__restrict__ S0)
 {
+    const int cpq = chunks_per_query(T);
     const int vec_per_tile = Ip / 16 * kTileRows;
     const long long total = (long long)n_pairs * chunks * vec_per_tile;
     for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < total;
@@ -754,12 +850,12 @@ __global__ void __launch_bounds__(256) raster_tiles_kernel(const uint8_t *__rest
         const long long tile_id = v / vec_per_tile;
         const int r = (int)(v - tile_id * vec_per_tile);
         const int kc = r / kTileRows, row = r - kc * kTileRows;
-        const int sp = row / kTileSteps, n = row - sp * kTileSteps;
+        const int sp = row & 1, n = row >> 1;                      // row = 2 * step + stream
         const int pr = (int)(tile_id / chunks), c = (int)(tile_id - (long long)pr * chunks);
-        const int b = 2 * pr + sp, step = c * kTileSteps + n;
+        const int b = 2 * pr + sp;
+        const int q = c / cpq, t = (c - q * cpq) * kTileSteps + n; // chunks never straddle a query
         uint32_t out[4] = {0u, 0u, 0u, 0u};
-        if (b < nb && step < steps) {
-            const int q = step / T, t = step - q * T;
+        if (b < nb && t < T && q < Q) {
             const uint8_t *px = pooled + ((size_t)b * Q + q) * I, *uq = Uq + (size_t)t * I;
             if ((I & 3) == 0) {     // rows are 4-byte aligned: word loads + byte-wise SIMD compare
                 const uint32_t *px4 = reinterpret_cast<const uint32_t *>(px) + kc * 4;
@@ -799,8 +895,11 @@ int snn_tc_prepare(SnnHandle *h, cudaStream_t st)
         h->P_tiles = ceil_div(h->P, tc::kM);
         const size_t bytes = (size_t)h->P_tiles * kPlanes * tc::kM * h->Fp;
         LENS_CUDA(cudaMalloc(&h->Wo_planes, bytes));
+        LENS_CUDA(cudaMalloc(&h->Wo_npl, (size_t)h->P_tiles * sizeof(int)));
+        tc::fill_int_kernel<<<ceil_div(h->P_tiles, 256), 256, 0, st>>>(h->Wo_npl, h->P_tiles, 5);
+        LENS_LAUNCH_CHECK();
         dim3 grid(h->P_tiles, h->Fp / 16);
-        tc::planes_kernel<<<grid, 128, 0, st>>>(h->Wo_fx, h->F, h->P, h->Fp, h->Wo_planes);
+        tc::planes_kernel<<<grid, 128, 0, st>>>(h->Wo_fx, h->F, h->P, h->Fp, h->Wo_planes, h->Wo_npl);
         LENS_LAUNCH_CHECK();
     }
     if (!h->Wf_planes && snn_tc_hidden_supported(h)) {
@@ -808,8 +907,11 @@ int snn_tc_prepare(SnnHandle *h, cudaStream_t st)
         h->F_tiles = ceil_div(h->F, tc::kM);
         const size_t bytes = (size_t)h->F_tiles * kPlanes * tc::kM * h->Ip;
         LENS_CUDA(cudaMalloc(&h->Wf_planes, bytes));
+        LENS_CUDA(cudaMalloc(&h->Wf_npl, (size_t)h->F_tiles * sizeof(int)));
+        tc::fill_int_kernel<<<ceil_div(h->F_tiles, 256), 256, 0, st>>>(h->Wf_npl, h->F_tiles, 5);
+        LENS_LAUNCH_CHECK();
         dim3 grid(h->F_tiles, h->Ip / 16);
-        tc::planes_kernel<<<grid, 128, 0, st>>>(h->Wf_fx, h->I, h->F, h->Ip, h->Wf_planes);
+        tc::planes_kernel<<<grid, 128, 0, st>>>(h->Wf_fx, h->I, h->F, h->Ip, h->Wf_planes, h->Wf_npl);
         LENS_LAUNCH_CHECK();
     }
     return 0;
@@ -819,8 +921,11 @@ void snn_tc_release(SnnHandle *h)
 {
     if (h->Wo_planes) cudaFree(h->Wo_planes);
     if (h->Wf_planes) cudaFree(h->Wf_planes);
+    if (h->Wo_npl) cudaFree(h->Wo_npl);
+    if (h->Wf_npl) cudaFree(h->Wf_npl);
     if (h->S0) cudaFree(h->S0);
-    h->Wo_planes = nullptr; h->Wf_planes = nullptr; h->S0 = nullptr; h->S0_cap = 0;
+    h->Wo_planes = nullptr; h->Wf_planes = nullptr; h->Wo_npl = nullptr; h->Wf_npl = nullptr;
+    h->S0 = nullptr; h->S0_cap = 0;
 }
 
 #define LENS_TC_LAUNCH_K(U, D, K, H)                                                                                 \
@@ -878,12 +983,15 @@ int snn_tc_output(SnnHandle *h, const int8_t *S1, int nb, int b0, int steps, flo
     p.planes = h->Wo_planes; p.S1 = S1; p.scale = h->Wo_scale;
     p.v2 = h->v2 + (size_t)b0 * h->P; p.counts = counts; p.out_steps = out_steps;
     p.P = h->P; p.Fp = h->Fp; p.T = h->T; p.steps = steps;
-    p.chunks = ceil_div(steps, kTileSteps); p.nb = nb; p.n_pairs = (nb + 1) / 2;
+    p.chunks = n_chunks_of(steps, h->T); p.nb = nb; p.n_pairs = (nb + 1) / 2;
+    p.npl = h->Wo_npl;
     p.thr = h->thr; p.vmin = h->vmin;
     const int sms = std::max(sm_count(), 1);
     p.n_tiles = h->P_tiles;
     const size_t smem = tc::smem_bytes(h->Fp);
-    dim3 grid((unsigned)std::min<long long>(sms, (long long)h->P_tiles * p.n_pairs));
+    unsigned grid_x = 1;
+    tc::schedule(p, sms, (size_t)p.chunks * s1_tile_bytes(h->Fp), grid_x);
+    dim3 grid(grid_x);
 #ifdef LENS_TC_PROFILE
     ProfDump prof_dump(grid.x, st, (long long)h->P_tiles * p.n_pairs * p.chunks / grid.x, "output");
     p.prof = prof_dump.d;
@@ -910,7 +1018,7 @@ int snn_tc_output(SnnHandle *h, const int8_t *S1, int nb, int b0, int steps, flo
 int snn_tc_hidden(SnnHandle *h, const uint8_t *pooled, int nb, int b0, int steps, uint8_t *hidden_steps,
                   cudaStream_t st)
 {
-    const int chunks = ceil_div(steps, kTileSteps), n_pairs = (nb + 1) / 2;
+    const int chunks = n_chunks_of(steps, h->T), n_pairs = (nb + 1) / 2;
     const size_t s0_bytes = (size_t)n_pairs * chunks * kTileRows * h->Ip;
     if (s0_bytes > h->S0_cap) {
         if (h->S0) LENS_CUDA(cudaFree(h->S0));
@@ -934,8 +1042,11 @@ int snn_tc_hidden(SnnHandle *h, const uint8_t *pooled, int nb, int b0, int steps
     p.S1_out = h->S1; p.out_Fp = h->Fp; p.overflow = h->counters;
     const int sms = std::max(sm_count(), 1);
     p.n_tiles = h->F_tiles;
+    p.npl = h->Wf_npl;
     const size_t smem = tc::smem_bytes(h->Ip, true);
-    dim3 grid((unsigned)std::min<long long>(sms, (long long)h->F_tiles * p.n_pairs));
+    unsigned grid_x = 1;
+    tc::schedule(p, sms, (size_t)chunks * s1_tile_bytes(h->Ip), grid_x);
+    dim3 grid(grid_x);
 #ifdef LENS_TC_PROFILE
     ProfDump prof_dump(grid.x, st, (long long)h->F_tiles * p.n_pairs * p.chunks / grid.x, "hidden");
     p.prof = prof_dump.d;

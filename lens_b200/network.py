@@ -16,6 +16,19 @@ from ._lib import check, ptr, stream_ptr, require_cuda, LensError
 from .ops import pool_geometry, pool_frames
 
 MODE_AUTO, MODE_SIMT, MODE_TC = 0, 1, 2
+MAX_SPIKES_PER_STEP = 127     # LENS_MAX_SPIKE: hidden spikes travel as int8 (sinabs' MultiSpike is unbounded)
+
+
+def _on_device(fn):
+    """Run a method with the network's device current, so the handle's launches, allocations and the
+    stream passed to the C ABI belong to that device whatever the caller's current device is."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *a, **kw):
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **kw)
+    return wrapped
 
 
 def raster_uniforms(T, roi, k, device):
@@ -59,6 +72,7 @@ class B200Network:
         self.max_streams = 0
         self._h = C.c_void_p()
         self.n_inexact = 0
+        self.check_overflow = True     # __call__ raises when a hidden neuron exceeded MAX_SPIKES_PER_STEP
         self._create(max_streams)
 
     # -- handle management ---------------------------------------------------------
@@ -73,6 +87,7 @@ class B200Network:
         self.max_streams = int(max_streams)
         self.n_inexact = int(n_inexact.value)
 
+    @_on_device
     def _destroy(self):
         if getattr(self, "_h", None) is not None and self._h.value:
             _lib.lib().lens_snn_destroy(self._h)
@@ -90,6 +105,7 @@ class B200Network:
             self._create(B)
 
     # -- sinabs-compatible surface ---------------------------------------------------
+    @_on_device
     def reset_states(self):
         check(_lib.lib().lens_snn_reset(self._h, stream_ptr()), "lens_snn_reset")
 
@@ -101,6 +117,7 @@ class B200Network:
             raise LensError("B200Network lives on a CUDA device")
         return self
 
+    @_on_device
     def __call__(self, x):
         """x f32 [T*B', 1, roi, roi] -> output spikes f32 [T*B', P] (lens/run_model.py:238)."""
         require_cuda(x)
@@ -117,11 +134,14 @@ class B200Network:
         out = torch.empty((Bp, self.T, self.P), dtype=torch.float32, device=x.device)
         check(_lib.lib().lens_snn_forward_float(self._h, ptr(xp), Bp, self.T, ptr(out), stream_ptr()),
               "lens_snn_forward_float")
+        if self.check_overflow:
+            self.raise_on_overflow()
         return out.reshape(n, self.P)
 
     forward = __call__
 
     # -- batched fast path -------------------------------------------------------------
+    @_on_device
     def run_streams(self, frames=None, pooled=None, mode=MODE_AUTO, want_steps=False):
         """Spike-count rows for B independent streams of Q queries.
 
@@ -148,6 +168,7 @@ class B200Network:
                                           int(mode), stream_ptr()), "lens_snn_forward")
         return (counts, hid, out) if want_steps else counts
 
+    @_on_device
     def run_streams_range(self, pooled, b0, counts, mode=MODE_AUTO):
         """Streams [b0, b0 + nb) only: pooled u8 [nb, Q, I] -> counts f32 [nb, Q, P] (pre-allocated).
 
@@ -162,6 +183,7 @@ class B200Network:
     def ensure_streams(self, B):
         self._ensure_streams(B)
 
+    @_on_device
     def state(self):
         """(v0 [B, I], v1 [B, F], v2 [B, P]) membrane potentials."""
         B = self.max_streams
@@ -172,9 +194,11 @@ class B200Network:
               "lens_snn_get_state")
         return v0, v1, v2
 
+    @_on_device
     def set_timing(self, enable=True):
         check(_lib.lib().lens_snn_set_timing(self._h, int(enable)), "lens_snn_set_timing")
 
+    @_on_device
     def get_timing(self):
         """-> dict(feature_ms, output_ms, n_feature, n_output) accumulated since the last call."""
         f, o = C.c_float(0), C.c_float(0)
@@ -183,7 +207,25 @@ class B200Network:
               "lens_snn_get_timing")
         return dict(feature_ms=f.value, output_ms=o.value, n_feature=nf.value, n_output=no.value)
 
+    @_on_device
+    def overflow_tensor(self):
+        """The overflow counter as a device tensor i64 [1] (stream-ordered copy, no synchronisation)."""
+        o = torch.zeros((1,), dtype=torch.int64, device=self.device)
+        check(_lib.lib().lens_snn_get_overflow(self._h, ptr(o), stream_ptr()), "lens_snn_get_overflow")
+        return o
+
+    @_on_device
     def overflow(self):
+        """Hidden-neuron steps whose spike count exceeded MAX_SPIKES_PER_STEP since the last reset
+        (clipped there; the reference's MultiSpike is unbounded, so a non-zero value means the spike
+        counts of this run are not the reference's).  Synchronises."""
         o = torch.zeros((1,), dtype=torch.int64, device=self.device)
         check(_lib.lib().lens_snn_get_overflow(self._h, ptr(o), stream_ptr()), "lens_snn_get_overflow")
         return int(o.item())
+
+    def raise_on_overflow(self):
+        n = self.overflow()
+        if n:
+            raise LensError(f"{n} hidden-neuron steps fired more than {MAX_SPIKES_PER_STEP} spikes in one "
+                            "timestep and were clipped (int8 spike transport): results would differ from the "
+                            "reference; call reset_states() and rescale the input")

@@ -27,6 +27,9 @@ class InferencePipeline:
                                device=device)
         self.L, self.n_top, self.ns, self.mode = int(L), int(n_top), tuple(ns), mode
         self.device = self.net.device
+        # optional per-stage CUDA-event timing (bench.py): [(start, after similarity, after match)]
+        self.stage_timing = False
+        self._stage_events = []
 
     def similarity(self, frames=None, pooled=None):
         """u8 frames [B, Q, roi, roi] (or pooled [B, Q, I]) -> spike counts f32 [B, Q, P]."""
@@ -44,9 +47,19 @@ class InferencePipeline:
 
     def step(self, frames=None, pooled=None, gt_dense=None, gt_center=None, gt_tol=0, reduce=True):
         """One pass of the hot path over this rank's shard; Recall counters all-reduced if distributed."""
+        ev = None
+        if self.stage_timing:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record()
         S = self.similarity(frames=frames, pooled=pooled)
+        if ev:
+            ev[1].record()
         out = self.match(S, gt_dense=gt_dense, gt_center=gt_center, gt_tol=gt_tol)
+        if ev:
+            ev[2].record()
+            self._stage_events.append(ev)
         out["S"] = S
+        out["overflow"] = self.net.overflow_tensor()   # device counter, no synchronisation: check with .item()
         if reduce and out["hits"] is not None and torch.distributed.is_available() \
                 and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
             packed = torch.cat([out["hits"], out["n_valid"]])
@@ -73,6 +86,9 @@ class InferencePipeline:
             self._slot ^= 1
             if self._stage[slot] is None or self._stage[slot].shape != src.shape:
                 self._stage[slot] = torch.empty(src.shape, dtype=torch.uint8, device=dev)
+                self._stage_free[slot] = None
+                # the allocator may hand back a block that kernels queued on the main stream still read
+                self._copy_stream.wait_stream(main)
             with torch.cuda.stream(self._copy_stream):
                 if self._stage_free[slot] is not None:
                     self._copy_stream.wait_event(self._stage_free[slot])   # last reader of this buffer
@@ -92,6 +108,15 @@ class InferencePipeline:
         if next_frames is not None:
             start_copy(next_frames)
         return out
+
+    def pop_stage_timing(self):
+        """-> dict(similarity_ms, match_ms, n) summed over the steps recorded since the last call."""
+        torch.cuda.synchronize(self.device)
+        sim = sum(a.elapsed_time(b) for a, b, _ in self._stage_events)
+        mat = sum(b.elapsed_time(c) for _, b, c in self._stage_events)
+        n = len(self._stage_events)
+        self._stage_events = []
+        return dict(similarity_ms=sim, match_ms=mat, n=n)
 
     @staticmethod
     def recall(hits, n_valid):

@@ -100,6 +100,7 @@ class LENS(nn.Module):
         self.build_network(max_streams=1)
         with torch.no_grad():
             S = self.similarity_matrix(test_loader)                 # [Q, P] f32, device
+        self.sinabs_model.raise_on_overflow()     # > 127 spikes of one neuron in one step: clipped, not the reference's
         Q, P = S.shape
         if (Q, P) != (model.query_places, model.reference_places):
             raise LensError(f"similarity matrix is {Q}x{P}, expected "

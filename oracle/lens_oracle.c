@@ -41,8 +41,9 @@
  *     imwrite(frame.astype(uint8))            -> counts wrap modulo 256
  * One frame per `window_us` slice of the time axis (collect_data.py:186-191
  * drains the sink every `timebin` ms).  Index -1 wraps to the last row/column
- * (torch negative indexing).  Events outside the ROI are cropped (on-chip ROI,
- * collect_data.py:230-233).  win_events[w] counts the in-ROI events of window
+ * (torch negative indexing).  Events whose shifted index lies outside the range
+ * the reference's tensor accepts, [-roi, roi-1], are cropped (on-chip ROI,
+ * collect_data.py:230-233; the Speck crop is 81 columns wide, so x == roi occurs).  win_events[w] counts the in-ROI events of window
  * w so the caller can drop empty windows like create_images does (:194).
  * frames: [n_win, roi, roi] u8, pooled (R1 applied): [n_win, dims*dims] u8.   */
 int lens_oracle_bin_events(const uint32_t *t_us, const uint16_t *x, const uint16_t *y,
@@ -66,9 +67,10 @@ int lens_oracle_bin_events(const uint32_t *t_us, const uint16_t *x, const uint16
         uint64_t hi = lo + window_us;
         while (e < n_events && (uint64_t)t_us[e] < lo) ++e; /* before t0: dropped */
         for (; e < n_events && (uint64_t)t_us[e] < hi; ++e) {
-            int xr = (int)x[e] - roi_x0, yr = (int)y[e] - roi_y0;
-            if (xr < 0 || xr >= roi || yr < 0 || yr >= roi) continue;
-            int col = xr - index_shift, row = yr - index_shift;
+            /* every index the reference's roi x roi tensor accepts: [-roi, roi-1], negatives wrap
+             * (x == roi lands in column roi-1 when index_shift is 1); the rest would raise IndexError */
+            int col = (int)x[e] - roi_x0 - index_shift, row = (int)y[e] - roi_y0 - index_shift;
+            if (col < -roi || col >= roi || row < -roi || row >= roi) continue;
             if (col < 0) col += roi;
             if (row < 0) row += roi;
             acc[(int64_t)row * roi + col] += 1;

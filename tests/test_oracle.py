@@ -136,26 +136,36 @@ def test_recall_variants(golden):
 
 
 def test_bin_events_reference_loop():
-    """Oracle binning == the literal per-event loop of collect_data.py:193-202."""
+    """Oracle binning == the literal per-event loop of collect_data.py:193-202, including the events at
+    x == roi / y == roi that the reference's `frame[y-1, x-1]` still accepts (the Speck crop is 81
+    columns wide); only indices the reference would raise IndexError on are cropped."""
     rng = np.random.default_rng(5)
     roi, n = 16, 4000
     t = np.sort(rng.integers(0, 1000, n)).astype(np.uint32)
-    x = rng.integers(0, roi, n).astype(np.uint16)
-    y = rng.integers(0, roi, n).astype(np.uint16)
+    x = rng.integers(0, roi + 3, n).astype(np.uint16)     # 0 .. roi + 2: roi is valid, roi + 1 is not
+    y = rng.integers(0, roi + 3, n).astype(np.uint16)
     x[:600] = 3
     y[:600] = 0   # > 255 hits on one pixel of window 0 -> uint8 wrap; y = 0 -> row -1
     t[:600] = 5
     t.sort()
     frames, pooled, cnt = O.bin_events(t, x, y, 0, 250, 4, roi, 4)
+    edge = 0
     for w in range(4):
         fr = np.zeros((roi, roi), dtype=np.int64)
         sel = (t >= 250 * w) & (t < 250 * (w + 1))
+        kept = 0
         for xe, ye in zip(x[sel].astype(int), y[sel].astype(int)):
-            fr[ye - 1, xe - 1] += 1
+            try:
+                fr[ye - 1, xe - 1] += 1
+                kept += 1
+                edge += xe == roi or ye == roi
+            except IndexError:
+                pass
         assert np.array_equal(frames[w], fr.astype(np.uint8))
-        assert cnt[w] == sel.sum()
+        assert cnt[w] == kept
+    assert edge > 50                       # the x == roi / y == roi column and row really are exercised
     assert np.array_equal(pooled, O.pool(frames, 4))
-    assert frames.astype(int).sum() != n   # the wrap really happened
+    assert frames.astype(int).sum() != cnt.sum()   # the wrap really happened
 
 
 def test_forward_float_matches_raster_path(golden):
