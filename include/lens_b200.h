@@ -153,6 +153,24 @@ int lens_recall(const int32_t *top_idx, int B, int Qo, int Po, int N, const uint
                 int64_t gt_stream_stride, const int32_t *gt_center, int gt_tol, const int *ns,
                 int n_ns, int64_t *hits, int64_t *n_valid, void *stream);
 
+/* Final top-N merge for a PLACE-sharded database (BASELINE config 5: "NCCL all-gather of database
+ * representations + top-N merge"): every shard ranks its own range of places with lens_seqmatch_topk, the
+ * W per-shard lists of a query are gathered, and the global list is the N best of their union under the
+ * same order as lens/src/metrics.py:218 under the deterministic rule (value desc, place index desc).
+ *   val, idx [W][M][N] device (idx = GLOBAL place index, -1 = empty slot), M = streams * queries,
+ *   out_val, out_idx [M][N] device.  W * N <= 512.                                                       */
+int lens_topn_merge(const float *val, const int32_t *idx, int W, int64_t M, int N, float *out_val,
+                    int32_t *out_idx, void *stream);
+
+/* Tie-aware bounds of Recall@N (lens/src/metrics.py:218 ranks with numpy's default, unstable argsort, so the
+ * reference's number is defined only up to the order of equal similarities): over every such order,
+ *   lo [n_ns] i64 device, ACCUMULATED: queries that hit in the top ns[i] whatever the order,
+ *   hi [n_ns] i64 device, ACCUMULATED: queries that hit for some order,
+ *   n_valid [1] i64 device, ACCUMULATED: queries with at least one positive (metrics.py:214-216).
+ * D, GT [Po][Qo] (rows = database, the matrices recallAtK receives), ns host ints ascending.          */
+int lens_recall_bounds(const float *D, const uint8_t *GT, int Po, int Qo, const int *ns, int n_ns,
+                       int64_t *lo, int64_t *hi, int64_t *n_valid, void *stream);
+
 /* Precision-recall counters of lens/src/metrics.py:21-139 (createPR, matching='single'), used by
  * lens/run_model.py:319-327 with n_thresh = 100.  S and GT are [Po][Qo] (rows = database), exactly the
  * matrices the reference passes (after its transposes).  Per query column the best match is the FIRST

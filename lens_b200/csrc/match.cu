@@ -21,6 +21,7 @@ namespace lens {
 constexpr int kMatchThreads = 256;
 constexpr int kCandChunk = 2048;
 constexpr int kMaxTopN = 64;
+constexpr int kUnrollR = 4;       // candidate batches (of 32 places) in flight per warp in the warp-per-query kernel
 
 __device__ __forceinline__ uint32_t f32_orderable(float v)
 {
@@ -137,37 +138,57 @@ seqmatch_topk_warp_kernel(const float *__restrict__ S, long long n_queries, int 
         const int b = (int)(g / Qo), q = (int)(g - (long long)b * Qo);
         const float *Sb = S + ((size_t)b * Q + q) * P;
         unsigned long long best = 0ull;                    // lane i: i-th largest key, 0 = empty
-        for (int r0 = 0; r0 < Po; r0 += 32) {
-            const int r = r0 + lane;
-            unsigned long long key = 0ull;
-            if (r < Po) {
-                float acc = 0.0f;
-                for (int j = 0; j < L; ++j) acc += __ldg(Sb + (size_t)j * P + (r + j));
-                const float d = __fdiv_rn(acc, fl);
-                if (D_out) D_out[((size_t)b * Po + r) * Qo + q] = d;
-                key = ((unsigned long long)f32_orderable(d) << 32) | (uint32_t)r;
-            }
-            const unsigned long long kth = shfl_u64(best, 31);          // current 32nd largest
-            if (!__any_sync(0xffffffffu, key > kth)) continue;          // nothing in this batch can enter
-            // bitonic sort of the batch, descending
+        // kUnrollR batches of 32 candidates per iteration: all their L x kUnrollR loads are issued before
+        // the first use, which is what keeps enough bytes in flight per warp to approach the HBM rate
+        for (int r0 = 0; r0 < Po; r0 += 32 * kUnrollR) {
+            float acc[kUnrollR];
 #pragma unroll
-            for (int k = 2; k <= 32; k <<= 1) {
+            for (int u = 0; u < kUnrollR; ++u) acc[u] = 0.0f;
+            if (r0 + 32 * kUnrollR <= Po) {
+                for (int j = 0; j < L; ++j) {
+                    const float *row = Sb + (size_t)j * P + (r0 + lane + j);
 #pragma unroll
-                for (int j = k >> 1; j > 0; j >>= 1) {
-                    const unsigned long long other = shfl_xor_u64(key, j);
-                    const bool take_max = (((lane & j) == 0) == ((lane & k) == 0));
-                    key = take_max ? (key > other ? key : other) : (key < other ? key : other);
+                    for (int u = 0; u < kUnrollR; ++u) acc[u] += __ldg(row + 32 * u);
+                }
+            } else {
+                for (int j = 0; j < L; ++j) {
+                    const float *row = Sb + (size_t)j * P + (r0 + lane + j);
+#pragma unroll
+                    for (int u = 0; u < kUnrollR; ++u)
+                        if (r0 + 32 * u + lane < Po) acc[u] += __ldg(row + 32 * u);
                 }
             }
-            // top 32 of (running list U batch): elementwise max against the reversed batch is bitonic
-            const unsigned long long rev = shfl_u64(key, 31 - lane);
-            unsigned long long c = best > rev ? best : rev;
 #pragma unroll
-            for (int j = 16; j > 0; j >>= 1) {
-                const unsigned long long other = shfl_xor_u64(c, j);
-                c = ((lane & j) == 0) ? (c > other ? c : other) : (c < other ? c : other);
+            for (int u = 0; u < kUnrollR; ++u) {
+                const int r = r0 + 32 * u + lane;
+                unsigned long long key = 0ull;
+                if (r < Po) {
+                    const float d = __fdiv_rn(acc[u], fl);
+                    if (D_out) D_out[((size_t)b * Po + r) * Qo + q] = d;
+                    key = ((unsigned long long)f32_orderable(d) << 32) | (uint32_t)r;
+                }
+                const unsigned long long kth = shfl_u64(best, 31);          // current 32nd largest
+                if (!__any_sync(0xffffffffu, key > kth)) continue;          // nothing in this batch can enter
+                // bitonic sort of the batch, descending
+#pragma unroll
+                for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+                    for (int j = k >> 1; j > 0; j >>= 1) {
+                        const unsigned long long other = shfl_xor_u64(key, j);
+                        const bool take_max = (((lane & j) == 0) == ((lane & k) == 0));
+                        key = take_max ? (key > other ? key : other) : (key < other ? key : other);
+                    }
+                }
+                // top 32 of (running list U batch): elementwise max against the reversed batch is bitonic
+                const unsigned long long rev = shfl_u64(key, 31 - lane);
+                unsigned long long c = best > rev ? best : rev;
+#pragma unroll
+                for (int j = 16; j > 0; j >>= 1) {
+                    const unsigned long long other = shfl_xor_u64(c, j);
+                    c = ((lane & j) == 0) ? (c > other ? c : other) : (c < other ? c : other);
+                }
+                best = c;
             }
-            best = c;
         }
         if (lane < N) {
             const size_t o = (size_t)g * N + lane;
@@ -178,6 +199,54 @@ seqmatch_topk_warp_kernel(const float *__restrict__ S, long long n_queries, int 
                 top_val[o] = f32_from_orderable((uint32_t)(best >> 32));
                 top_idx[o] = (int32_t)(uint32_t)(best & 0xffffffffull);
             }
+        }
+    }
+}
+
+// Final merge of per-shard top-N lists (place-sharded database, BASELINE config 5): every rank ranks its own
+// range of places, the W lists of a query are all-gathered, and the global top-N is the N best of their
+// union under the same order (value desc, place index desc).  One warp per query; the <= W*N candidate keys
+// sit in registers (kMergeSlots per lane), N rounds of warp-wide 64-bit max.
+constexpr int kMergeSlots = 16;      // W * N <= 32 * kMergeSlots
+
+__global__ void __launch_bounds__(256) topn_merge_kernel(const float *__restrict__ val, const int32_t *__restrict__ idx,
+                                                         int W, long long M, int N, float *__restrict__ out_val,
+                                                         int32_t *__restrict__ out_idx)
+{
+    const int lane = threadIdx.x & 31;
+    const long long m = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    if (m >= M) return;
+    const int n_cand = W * N;
+    unsigned long long key[kMergeSlots];
+#pragma unroll
+    for (int s = 0; s < kMergeSlots; ++s) {
+        const int c = s * 32 + lane;
+        key[s] = 0ull;
+        if (c < n_cand) {
+            const int w = c / N, n = c - w * N;
+            const size_t o = ((size_t)w * M + m) * N + n;
+            const int32_t i = idx[o];
+            if (i >= 0) key[s] = ((unsigned long long)f32_orderable(val[o]) << 32) | (uint32_t)i;
+        }
+    }
+    for (int n = 0; n < N; ++n) {
+        unsigned long long mine = 0ull;
+#pragma unroll
+        for (int s = 0; s < kMergeSlots; ++s) mine = key[s] > mine ? key[s] : mine;
+        unsigned long long best = mine;
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = shfl_xor_u64(best, o);
+            best = other > best ? other : best;
+        }
+        if (best != 0ull && mine == best) {            // keys are unique (distinct place indices): one owner
+#pragma unroll
+            for (int s = 0; s < kMergeSlots; ++s)
+                if (key[s] == best) key[s] = 0ull;
+        }
+        if (lane == 0) {
+            const size_t o = (size_t)m * N + n;
+            out_val[o] = best ? f32_from_orderable((uint32_t)(best >> 32)) : -INFINITY;
+            out_idx[o] = best ? (int32_t)(uint32_t)(best & 0xffffffffull) : -1;
         }
     }
 }
@@ -237,6 +306,74 @@ __global__ void __launch_bounds__(256) recall_kernel(RecallParams p)
     if (threadIdx.x < p.n_ns && s_hits[threadIdx.x])
         atomicAdd(p.hits + threadIdx.x, (unsigned long long)s_hits[threadIdx.x]);
     if (threadIdx.x == 0 && s_valid) atomicAdd(p.n_valid, (unsigned long long)s_valid);
+}
+
+// Tie-aware bounds of Recall@K: lens/src/metrics.py:218 ranks every query column with numpy's
+// default argsort, which is free to order equal similarities either way, so the reference's own number
+// is only defined up to the choice among ties.  One warp per query column walks the distinct similarity
+// values from the top: g = entries strictly above the current value (all of them are in any top-K with
+// K > g), c = entries equal to it.  For the K whose K-th entry falls on this value (g < K <= g + c):
+//   certain hit  <=> a positive lies strictly above, or the K - g picks among the c ties cannot avoid one
+//   possible hit <=> a positive lies strictly above or among the ties.
+struct BoundsParams {
+    const float *D;            // [Po][Qo]
+    const uint8_t *GT;         // [Po][Qo]
+    int Po, Qo, n_ns;
+    int ns[8];
+    unsigned long long *lo, *hi, *n_valid;
+};
+
+__global__ void __launch_bounds__(256) recall_bounds_kernel(BoundsParams p)
+{
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= p.Qo) return;
+    int any = 0;
+    for (int r = lane; r < p.Po; r += 32) any |= p.GT[(size_t)r * p.Qo + q] != 0;
+    if (!__any_sync(0xffffffffu, any)) return;                   // metrics.py:214-216: no positive, dropped
+    const int kmax = p.ns[p.n_ns - 1];
+    float cur = INFINITY;
+    int g = 0, gpos = 0, next_k = 0;                              // next_k: first K not decided yet
+    unsigned lo_mask = 0u, hi_mask = 0u;
+    while (next_k < p.n_ns) {
+        // largest value strictly below `cur`, its multiplicity and its positives
+        float m = -INFINITY;
+        for (int r = lane; r < p.Po; r += 32) {
+            const float v = p.D[(size_t)r * p.Qo + q];
+            if (v < cur) m = fmaxf(m, v);
+        }
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        int c = 0, cpos = 0;
+        for (int r = lane; r < p.Po; r += 32) {
+            const float v = p.D[(size_t)r * p.Qo + q];
+            if (v == m && v < cur) { ++c; cpos += p.GT[(size_t)r * p.Qo + q] != 0; }
+        }
+        c = __reduce_add_sync(0xffffffffu, c);
+        cpos = __reduce_add_sync(0xffffffffu, cpos);
+        if (c == 0) {
+            // the column is exhausted (K > Po, or only NaNs are left): everything ranked so far is certain
+            for (; next_k < p.n_ns; ++next_k)
+                if (gpos > 0) { lo_mask |= 1u << next_k; hi_mask |= 1u << next_k; }
+            break;
+        }
+        for (; next_k < p.n_ns && p.ns[next_k] <= g + c; ++next_k) {
+            const int room = p.ns[next_k] - g;                    // picks among the c ties
+            if (gpos > 0) { lo_mask |= 1u << next_k; hi_mask |= 1u << next_k; }
+            else if (cpos > 0) {
+                hi_mask |= 1u << next_k;
+                if (c - cpos < room) lo_mask |= 1u << next_k;
+            }
+        }
+        g += c; gpos += cpos; cur = m;
+        if (g >= kmax) break;
+    }
+    if (lane == 0) {
+        atomicAdd(p.n_valid, 1ull);
+        for (int i = 0; i < p.n_ns; ++i) {
+            if (lo_mask >> i & 1u) atomicAdd(p.lo + i, 1ull);
+            if (hi_mask >> i & 1u) atomicAdd(p.hi + i, 1ull);
+        }
+    }
 }
 
 // createPR, matching = 'single' (lens/src/metrics.py:21-139): one CTA, columns strided over threads.
@@ -476,6 +613,40 @@ extern "C" int lens_recall(const int32_t *top_idx, int B, int Qo, int Po, int N,
     if (B == 0) return 0;
     int64_t total = (int64_t)B * Qo;
     recall_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, as_stream(stream)>>>(p);
+    LENS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int lens_recall_bounds(const float *D, const uint8_t *GT, int Po, int Qo, const int *ns, int n_ns,
+                                  int64_t *lo, int64_t *hi, int64_t *n_valid, void *stream)
+{
+    LENS_CHECK_ARG(Po > 0 && Qo > 0, "lens_recall_bounds: bad sizes");
+    LENS_CHECK_ARG(D && GT && lo && hi && n_valid, "lens_recall_bounds: NULL buffer");
+    LENS_CHECK_ARG(ns && n_ns >= 1 && n_ns <= 8, "lens_recall_bounds: n_ns must be in [1, 8]");
+    BoundsParams p;
+    p.D = D; p.GT = GT; p.Po = Po; p.Qo = Qo; p.n_ns = n_ns;
+    for (int i = 0; i < 8; ++i) p.ns[i] = 0;
+    for (int i = 0; i < n_ns; ++i) {
+        LENS_CHECK_ARG(ns[i] >= 1 && (i == 0 || ns[i] > ns[i - 1]), "lens_recall_bounds: ns must be ascending and >= 1");
+        p.ns[i] = ns[i];
+    }
+    p.lo = reinterpret_cast<unsigned long long *>(lo);
+    p.hi = reinterpret_cast<unsigned long long *>(hi);
+    p.n_valid = reinterpret_cast<unsigned long long *>(n_valid);
+    recall_bounds_kernel<<<(unsigned)ceil_div(Qo, 8), 256, 0, as_stream(stream)>>>(p);
+    LENS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int lens_topn_merge(const float *val, const int32_t *idx, int W, int64_t M, int N, float *out_val,
+                               int32_t *out_idx, void *stream)
+{
+    LENS_CHECK_ARG(W >= 1 && M >= 0 && N >= 1, "lens_topn_merge: bad sizes");
+    LENS_CHECK_ARG((int64_t)W * N <= 32 * kMergeSlots, "lens_topn_merge: W * N = %lld exceeds %d", (long long)W * N,
+                   32 * kMergeSlots);
+    if (M == 0) return 0;
+    LENS_CHECK_ARG(val && idx && out_val && out_idx, "lens_topn_merge: NULL buffer");
+    topn_merge_kernel<<<(unsigned)ceil_div64(M, 8), 256, 0, as_stream(stream)>>>(val, idx, W, M, N, out_val, out_idx);
     LENS_LAUNCH_CHECK();
     return 0;
 }

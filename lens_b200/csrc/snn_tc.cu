@@ -54,9 +54,9 @@ constexpr int kDrainGroups = 2;         // drain warpgroups; each owns kN / kDra
 constexpr int kNd = kN / kDrainGroups;  // (= the 32 steps of one stream)
 constexpr int kScanWarp0 = 4 + 4 * kDrainGroups;
 constexpr int kThreads = 128 * (2 + kDrainGroups);   // control + drain warpgroups + scan
-constexpr int kRegsControl = 56;        // setmaxnreg budgets: 128 * (56 + 2 * 176 + 104) = 512 * 128
-constexpr int kRegsDrain = 176;
-constexpr int kRegsScan = 104;
+constexpr int kRegsControl = 56;        // setmaxnreg budgets: 128 * (56 + 2 * 168 + 120) = 512 * 128
+constexpr int kRegsDrain = 168;
+constexpr int kRegsScan = 120;
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
     return (uint32_t)__cvta_generic_to_shared(p);
@@ -486,7 +486,6 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
         const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((warp - 4) >> 2) * kNd;
         int it = 0;
         uint32_t probe0 = 0;
-        bool preloaded = false;     // the coming tile's first loads (pair 0, columns 0..15) are already in flight
         PROF_DECL;
         for (int u = blockIdx.x; u < p.n_super; u += gridDim.x) {
         const int pb = u / p.n_tiles, tile = u - pb * p.n_tiles;
@@ -497,8 +496,7 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
         for (int i = 0; i < n_it; ++i, ++it) {
             // X = sum_j P_j 256^j as (xh:xl) for the kNd columns of this lane.  The (pair, 16-column) loads
             // are double-buffered in registers: the tcgen05.ld of step s + 1 is in flight while step s is
-            // folded into X, and the first load of the NEXT tile is issued before the last fold and the
-            // int64 -> fp32 conversions (XU pipe), which hide its latency.
+            // folded into X, so only the first load's latency is exposed.
             int32_t xl[kNd], xh[kNd];
             int32_t buf[2][32];
             uint32_t probe = 0;
@@ -507,20 +505,15 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
             static_assert(kH == 2, "the drain schedule below assumes two 16-column halves per warpgroup");
             PROF(1);
             GANTT(16);
-            if (!preloaded) {
-                mbar_wait_probed(probe0, acc_full + 0, it & 1);
-                tc_fence_after();
-            }
+            mbar_wait_probed(probe0, acc_full + 0, it & 1);
+            tc_fence_after();
             // in steady state the MMA warps are a tile ahead: poll the other two pairs now, so that the
             // polls' latency hides behind the first pair's loads and folding
             const uint32_t probe1 = mbar_probe(acc_full + 1, it & 1), probe2 = mbar_probe(acc_full + 2, it & 1);
             PROF(0);
             GANTT(17);
-            if (!preloaded) {
-                tmem_ld16(tlane + 0 * kN, reinterpret_cast<int32_t(&)[16]>(buf[0][0]));
-                tmem_ld16(tlane + 1 * kN, reinterpret_cast<int32_t(&)[16]>(buf[0][16]));
-            }
-            preloaded = false;
+            tmem_ld16(tlane + 0 * kN, reinterpret_cast<int32_t(&)[16]>(buf[0][0]));
+            tmem_ld16(tlane + 1 * kN, reinterpret_cast<int32_t(&)[16]>(buf[0][16]));
 #pragma unroll
             for (int s = 0; s < kSteps; ++s) {
                 const int g = s / kH, h = s % kH;
@@ -549,19 +542,7 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
                     tmem_ld16(tlane + (2 * g2) * kN + h2 * 16, reinterpret_cast<int32_t(&)[16]>(buf[(s + 1) & 1][0]));
                     if (g2 < 2 || top2)
                         tmem_ld16(tlane + (2 * g2 + 1) * kN + h2 * 16, reinterpret_cast<int32_t(&)[16]>(buf[(s + 1) & 1][16]));
-                    if (s + 1 == 2 * kH) {
-                        probe = mbar_probe(x_empty + (it & 1), ((it >> 1) & 1) ^ 1);
-                        probe0 = mbar_probe(acc_full + 0, (it + 1) & 1);        // next tile's first pair
-                    }
-                } else {
-                    // last step: start the next tile's first loads (pair 0, columns 0..15) into the free buffer
-                    const bool more = (i + 1 < n_it) || (u + (int)gridDim.x < p.n_super);
-                    if (more && (probe0 || mbar_probe(acc_full + 0, (it + 1) & 1))) {
-                        tc_fence_after();
-                        tmem_ld16(tlane + 0 * kN, reinterpret_cast<int32_t(&)[16]>(buf[0][0]));
-                        tmem_ld16(tlane + 1 * kN, reinterpret_cast<int32_t(&)[16]>(buf[0][16]));
-                        preloaded = true;
-                    }
+                    if (s + 1 == 2 * kH) probe = mbar_probe(x_empty + (it & 1), ((it >> 1) & 1) ^ 1);
                 }
                 if (g == 2 && !top2) {
 #pragma unroll
@@ -589,6 +570,7 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
             tc_fence_after();
             PROF(2);
             GANTT(23);
+            probe0 = mbar_probe(acc_full + 0, (it + 1) & 1);        // next tile's first pair
 #pragma unroll
             for (int h = 0; h < kH; ++h) {
                 float xf[16];

@@ -105,6 +105,38 @@ def recall_counts(top_idx, Po, gt_dense=None, gt_center=None, gt_tol=0, ns=RECAL
     return hits, n_valid
 
 
+def topn_merge(vals, idx):
+    """Global top-N from W per-shard lists: vals f32 / idx i32 [W, B, Qo, N] (idx = global place index, -1 =
+    empty) -> (val [B, Qo, N], idx [B, Qo, N]) under the order (value desc, place index desc)."""
+    require_cuda(vals, idx)
+    assert vals.dtype == torch.float32 and idx.dtype == torch.int32 and vals.shape == idx.shape and vals.dim() == 4
+    vals, idx = vals.contiguous(), idx.contiguous()
+    W, B, Qo, N = vals.shape
+    ov = torch.empty((B, Qo, N), dtype=torch.float32, device=vals.device)
+    oi = torch.empty((B, Qo, N), dtype=torch.int32, device=vals.device)
+    check(_lib.lib().lens_topn_merge(ptr(vals), ptr(idx), W, B * Qo, N, ptr(ov), ptr(oi), stream_ptr()),
+          "lens_topn_merge")
+    return ov, oi
+
+
+def recall_bounds(D, gt_dense, ns=RECALL_NS):
+    """Tie-aware (lo, hi, n_valid) hit counters of Recall@N over every order of equal similarities.
+
+    D f32 [Po, Qo], gt_dense u8 [Po, Qo] (rows = database) -> (lo [len(ns)] i64, hi, n_valid [1]) on the device;
+    lo / n_valid <= the reference's recallAtK (numpy's unstable argsort, metrics.py:218) <= hi / n_valid."""
+    require_cuda(D, gt_dense)
+    assert D.dtype == torch.float32 and gt_dense.dtype == torch.uint8 and D.shape == gt_dense.shape and D.dim() == 2
+    D, gt_dense = D.contiguous(), gt_dense.contiguous()
+    Po, Qo = D.shape
+    lo = torch.zeros((len(ns),), dtype=torch.int64, device=D.device)
+    hi = torch.zeros((len(ns),), dtype=torch.int64, device=D.device)
+    n_valid = torch.zeros((1,), dtype=torch.int64, device=D.device)
+    ns_arr = (C.c_int * len(ns))(*ns)
+    check(_lib.lib().lens_recall_bounds(ptr(D), ptr(gt_dense), Po, Qo, ns_arr, len(ns), ptr(lo), ptr(hi), ptr(n_valid),
+                                        stream_ptr()), "lens_recall_bounds")
+    return lo, hi, n_valid
+
+
 def sad_matrix(query_frames, reference_frames):
     """u8 [Q, npix], u8 [R, npix] -> L1 distances f32 [Q, R] (torch.cdist(a, b, 1) of lens/src/sad.py:38)."""
     require_cuda(query_frames, reference_frames)

@@ -20,6 +20,15 @@ def shard_range(n, rank, world):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def place_shard_range(P, L, rank, world):
+    """Places a rank holds when the DATABASE is sharded: its own contiguous range [p0, p1) of the
+    P - L + 1 sequence-matched rows plus the L - 1 places after it (every diagonal that starts in the
+    range is complete without an exchange).  -> (p0, p1, p1_with_halo)."""
+    Po = P - max(L, 1) + 1
+    p0, p1 = shard_range(Po, rank, world)
+    return p0, p1, min(P, p1 + max(L, 1) - 1)
+
+
 class InferencePipeline:
     def __init__(self, W_feat, W_out, roi, k, T, L, n_top=25, ns=ops.RECALL_NS, max_streams=1,
                  device=None, mode=MODE_AUTO):
@@ -122,3 +131,43 @@ class InferencePipeline:
     def recall(hits, n_valid):
         nv = int(n_valid.item())
         return [float(h) / nv if nv else float("nan") for h in hits.tolist()]
+
+
+class PlaceShardedPipeline:
+    """The same hot path with the DATABASE sharded across ranks instead of the streams (the
+    alternative for few streams / very large databases): every rank runs ALL streams against its own range
+    of places (output layer is column-parallel; the tiny feature layer is replicated), ranks them locally,
+    and the per-rank top-N lists are all-gathered (NCCL) and merged on the GPU (lens_topn_merge).  The merged
+    lists equal the single-GPU lists bit for bit: the order (value desc, place index desc) is global."""
+
+    def __init__(self, W_feat, W_out, roi, k, T, L, n_top=25, ns=ops.RECALL_NS, max_streams=1, device=None,
+                 mode=MODE_AUTO, rank=None, world=None):
+        import torch.distributed as dist
+        self.dist = dist if (dist.is_available() and dist.is_initialized()) else None
+        self.rank = rank if rank is not None else (self.dist.get_rank() if self.dist else 0)
+        self.world = world if world is not None else (self.dist.get_world_size() if self.dist else 1)
+        self.P = int(W_out.shape[0])
+        self.L, self.n_top, self.ns, self.mode = int(L), int(n_top), tuple(ns), mode
+        self.p0, self.p1, p1h = place_shard_range(self.P, self.L, self.rank, self.world)
+        self.net = B200Network(W_feat, W_out[self.p0:p1h], roi=roi, k=k, num_timesteps=T, max_streams=max_streams,
+                               device=device)
+        self.device = self.net.device
+
+    def step(self, frames=None, pooled=None, gt_center=None, gt_tol=0):
+        """-> dict(top_val, top_idx (global place indices), hits, n_valid); every rank holds the merged result."""
+        S = self.net.run_streams(frames=frames, pooled=pooled, mode=self.mode)       # [B, Q, local places + halo]
+        tv, ti, _ = ops.seqmatch_topk(S, self.L, self.n_top)
+        ti = torch.where(ti >= 0, ti + self.p0, ti)
+        if self.world > 1:
+            allv = torch.empty((self.world,) + tuple(tv.shape), dtype=tv.dtype, device=tv.device)
+            alli = torch.empty((self.world,) + tuple(ti.shape), dtype=ti.dtype, device=ti.device)
+            self.dist.all_gather_into_tensor(allv, tv.contiguous())
+            self.dist.all_gather_into_tensor(alli, ti.contiguous())
+        else:
+            allv, alli = tv[None], ti[None]
+        tv, ti = ops.topn_merge(allv, alli)
+        out = dict(top_val=tv, top_idx=ti, hits=None, n_valid=None)
+        if gt_center is not None:
+            out["hits"], out["n_valid"] = ops.recall_counts(ti, self.P - self.L + 1, gt_center=gt_center,
+                                                            gt_tol=gt_tol, ns=self.ns)
+        return out

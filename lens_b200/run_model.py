@@ -21,7 +21,7 @@ from .network import B200Network
 from .src import blitnet as bn
 from .src.dataset import CustomImageDataset, ProcessImage
 from .src.loggers import model_logger
-from .src.metrics import recallAtK, createPR  # noqa: F401  (re-exported like the reference module)
+from .src.metrics import recallAtK, createPR, recall_detail  # noqa: F401  (re-exported like the reference module)
 
 RECALL_NS = [1, 5, 10, 15, 20, 25]   # run_model.py:266
 
@@ -62,6 +62,8 @@ class LENS(nn.Module):
         self.sinabs_model = None
         self.similarity = None        # [Q, P] spike counts of the last evaluate()
         self.dist_matrix_seq = None   # sequence-matched matrix of the last evaluate()
+        self.recall_gpu = None        # Recall@N under the CUDA kernel's deterministic tie rule
+        self.recall_bounds = None     # [(lo, hi)] over every order of equal similarities
 
     def add_layer(self, name, **kwargs):
         if name in self.layer_dict:
@@ -110,10 +112,12 @@ class LENS(nn.Module):
         n_top = max(RECALL_NS)
         if L != 0:
             _, top_idx, D = ops.seqmatch_topk(S[None].contiguous(), L, n_top, want_D=True)
-            dist_matrix_seq = D[0].cpu().numpy()                    # [P-L+1, Q-L+1], rows = database
+            D_dev = D[0]
+            dist_matrix_seq = D_dev.cpu().numpy()                   # [P-L+1, Q-L+1], rows = database
         else:
             # run_model.py:254 keeps `out` itself (rows = query) and ranks along axis 0
             _, top_idx, _ = ops.seqmatch_topk(S.t().contiguous()[None], 1, n_top)
+            D_dev = S
             dist_matrix_seq = S.cpu().numpy().astype(np.float64)
         self.dist_matrix_seq = dist_matrix_seq
         self._save_matrix_pdf(dist_matrix_seq, "distance_matrix_lens.pdf")
@@ -130,12 +134,18 @@ class LENS(nn.Module):
             # the reference fails inside recallAtK with this very assertion (metrics.py:196), e.g. for
             # --sequence_length 1, whose GT slice GT[-1:-1] is empty
             assert GTtol.shape == dist_matrix_seq.shape, "S_in and GThard must have the same shape"
-            gt = torch.from_numpy(np.ascontiguousarray(GTtol, dtype=np.uint8)).to(self.device)
-            hits, n_valid = ops.recall_counts(top_idx, GTtol.shape[0], gt_dense=gt, ns=tuple(RECALL_NS))
-            hits, n_valid = hits.cpu().numpy(), int(n_valid.item())
-            R = [round(float(h) / n_valid, 2) if n_valid else float("nan") for h in hits]
+            # Recall@N on the GPU: deterministic tie rule + bounds over every tie order.  Where the bounds
+            # differ, the reference's number depends on how numpy's unstable argsort orders equal
+            # similarities (metrics.py:218); that order is then taken from the same numpy call.
+            det = recall_detail(dist_matrix_seq, GTtol.astype(bool), RECALL_NS, top_idx=top_idx, S_dev=D_dev)
+            self.recall_gpu = [round(r, 2) for r in det["gpu"]]
+            self.recall_bounds = [(round(a, 2), round(b, 2)) for a, b in zip(det["lo"], det["hi"])]
+            R = [round(r, 2) for r in det["reference"]]
             model.logger.info("N      " + "  ".join(f"{n:>5d}" for n in RECALL_NS))
             model.logger.info("Recall " + "  ".join(f"{r:>5.2f}" for r in R))
+            if det["ties_decided"]:
+                model.logger.info("ties decide Recall@%s: GPU tie rule %s, bounds %s" %
+                                  (det["ties_decided"], self.recall_gpu, self.recall_bounds))
         self.GTtol = GTtol
 
         if getattr(self, "PR_curve", False):
