@@ -468,6 +468,53 @@ def measure_snn(ctx, c, steps, warmup, W_out_sharded=False, want_e2e=True):
     return res
 
 
+def measure_place_sharded(ctx, c, steps):
+    """Config 5 the other way round: the DATABASE is sharded (P / N places + L - 1 halo per rank), every rank
+    runs all streams of the job against its shard, the per-rank top-N lists are all-gathered over NCCL and
+    merged on the GPU (lens_topn_merge).  Reports the whole step and the collective + merge part alone."""
+    torch, dist = ctx.torch, ctx.dist
+    from lens_b200 import synth, ops
+    from lens_b200.pipeline import PlaceShardedPipeline
+    dev, world, rank = ctx.dev, ctx.world, ctx.rank
+    B, Q, L, P = c["streams_total"], c["queries"], c["seq_len"], c["places"]
+    I, F = I_DIMS * I_DIMS, FEATURE
+    Wf, Wo = synth.weights(I, F, P, seed=6)
+    pipe = PlaceShardedPipeline(torch.from_numpy(Wf), torch.from_numpy(Wo), roi=ROI, k=K_POOL, T=T_STEPS, L=L,
+                                n_top=N_TOP, ns=NS, max_streams=B, device=dev, mode=ctx.args.mode)
+    frames = synth.frames_device(B, Q, ROI, seed=2, device=dev)           # every rank sees every stream
+    gt = torch.from_numpy(synth.gt_centers(B, Q - L + 1, P - L + 1, seed=7)).to(dev)
+    for _ in range(3):
+        out = pipe.step(frames=frames, gt_center=gt, gt_tol=2)
+    ctx.barrier()
+    ms = ctx.timed(lambda: pipe.step(frames=frames, gt_center=gt, gt_tol=2), steps)
+    ctx.barrier()
+    # the exchange alone: all-gather of (value, index) lists + merge
+    tv, ti = out["top_val"].contiguous(), out["top_idx"].contiguous()
+    allv = torch.empty((world,) + tuple(tv.shape), dtype=tv.dtype, device=dev)
+    alli = torch.empty((world,) + tuple(ti.shape), dtype=ti.dtype, device=dev)
+
+    def exchange():
+        if world > 1:
+            dist.all_gather_into_tensor(allv, tv)
+            dist.all_gather_into_tensor(alli, ti)
+        return ops.topn_merge(allv, alli)
+    if world == 1:
+        allv.copy_(tv[None]); alli.copy_(ti[None])
+    for _ in range(3):
+        exchange()
+    ctx.barrier()
+    xms = ctx.timed(exchange, 5)
+    tot, xt = ctx.max_over_ranks(sum(ms), float(np.mean(xms)))
+    del pipe, frames
+    torch.cuda.empty_cache()
+    return dict(workload="%s, database sharded: %d places/GPU (+%d halo), all %d streams on every GPU" %
+                         (c["name"], P // world, L - 1, B),
+                value=B * Q * T_STEPS * steps / (tot / 1e3), unit="query_timesteps/s", ms_per_step=tot / steps,
+                topn_exchange=dict(ms=xt, bytes_gathered=int(allv.numel() * 8),
+                                   collective="2 x ncclAllGather (top-N values, indices) + lens_topn_merge"),
+                recall_at_n=dict(zip(map(str, NS), (out["hits"].double() / max(int(out["n_valid"].item()), 1)).tolist())))
+
+
 def measure_latency(ctx, c, reps=5):
     """Config 1: ONE stream, serial chain of Q*T steps through the public batched call; us per step."""
     torch = ctx.torch
@@ -584,6 +631,8 @@ def main():
                     m = measure_snn(ctx, ck, min(ksteps, 3), 3, W_out_sharded=True, want_e2e=False)
                     m["config"] = workload_config(ck, world)
                     extras["config5"] = m
+                    if world > 1:
+                        extras["config5_place_sharded"] = measure_place_sharded(ctx, ck, min(ksteps, 3))
             except Exception as e:                                   # an extra must never cost the main line
                 extras["config%d_error" % k] = repr(e)[:300]
     if "config4_binning" in extras:

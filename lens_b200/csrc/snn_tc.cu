@@ -52,7 +52,7 @@ constexpr int kTmemCols = 512;          // 6 planes x 64 accumulator columns + 2
 constexpr int kXCol = kPlanes * kN;     // first exchange column
 constexpr int kDrainGroups = 2;         // drain warpgroups; each owns kN / kDrainGroups accumulator columns
 constexpr int kNd = kN / kDrainGroups;  // (= the 32 steps of one stream)
-constexpr int kScanWarp0 = 4 + 4 * kDrainGroups;
+constexpr int kDrainWarp0 = 4, kScanWarp0 = 4 + 4 * kDrainGroups;   // warps 0-3 control, then drain, drain, scan
 constexpr int kThreads = 128 * (2 + kDrainGroups);   // control + drain warpgroups + scan
 constexpr int kRegsControl = 56;        // setmaxnreg budgets: 128 * (56 + 2 * 168 + 120) = 512 * 128
 constexpr int kRegsDrain = 168;
@@ -278,13 +278,16 @@ __device__ __forceinline__ float iaf_out(float &v, float x, float thr, float vmi
 // csum accumulates c (steps WITHOUT a spike); amax = largest pre-spike potential of the tile, which
 // decides afterwards whether some step left the fast path's domain (a >= 2).
 template <bool kRagged>
-__device__ __forceinline__ void scan_tile_unit(const float (&x)[kN], int nvalid, float2 &v, float2 &csum, float &amax)
+__device__ __forceinline__ void scan_tile_unit(const float (&x)[kN], float scale, int nvalid, float2 &v, float2 &csum,
+                                               float &amax)
 {
-    const float2 m1 = make_float2(-1.0f, -1.0f);
+    const float2 m1 = make_float2(-1.0f, -1.0f), sc = make_float2(scale, scale);
 #pragma unroll
     for (int n = 0; n < kTileSteps; ++n) {
         if (!kRagged || n < nvalid) {
-            const float2 a = __fadd2_rn(v, make_float2(x[2 * n], x[2 * n + 1]));
+            // x arrives as the rounded integer sum; scale = 2^q, so x * scale is exact and the FMA rounds once,
+            // exactly like fl(v + fl(x * scale))
+            const float2 a = __ffma2_rn(make_float2(x[2 * n], x[2 * n + 1]), sc, v);
             const float2 c = make_float2(a.x >= 1.0f ? 0.0f : 1.0f, a.y >= 1.0f ? 0.0f : 1.0f);
             const float2 lo = make_float2(fmaxf(a.x, -1.0f), fmaxf(a.y, -1.0f));
             amax = fmax3(amax, a.x, a.y);
@@ -300,14 +303,15 @@ __device__ __forceinline__ void scan_tile_unit(const float (&x)[kN], int nvalid,
 // relu(fl(a + (1 - s))) - 1 rounds like the reference's three operations.  The spike bytes go to the
 // staging tile rows 2n (even stream) and 2n + 1 (odd stream) of this lane's k-chunk.
 template <bool kRagged>
-__device__ __forceinline__ void scan_tile_hidden(const float (&x)[kN], int nvalid, float2 &v, float &amax, uint8_t *stage_out)
+__device__ __forceinline__ void scan_tile_hidden(const float (&x)[kN], float scale, int nvalid, float2 &v, float &amax,
+                                                 uint8_t *stage_out)
 {
     const float2 m1 = make_float2(-1.0f, -1.0f), big = make_float2(8388608.0f, 8388608.0f);
-    const float2 big1 = make_float2(8388609.0f, 8388609.0f);
+    const float2 big1 = make_float2(8388609.0f, 8388609.0f), sc = make_float2(scale, scale);
 #pragma unroll
     for (int n = 0; n < kTileSteps; ++n) {
         if (!kRagged || n < nvalid) {
-            const float2 a = __fadd2_rn(v, make_float2(x[2 * n], x[2 * n + 1]));
+            const float2 a = __ffma2_rn(make_float2(x[2 * n], x[2 * n + 1]), sc, v);   // exact product, one rounding
             const float2 ta = __fadd2_rz(make_float2(fmaxf(a.x, 0.0f), fmaxf(a.y, 0.0f)), big);
             amax = fmax3(amax, a.x, a.y);
             const float2 r = __fadd2_rn(a, __ffma2_rn(ta, m1, big1));       // a + (1 - s)
@@ -478,12 +482,12 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
         }
         if (warp == 1) PROF_FLUSH(0);
     }
-    } else if (warp < kScanWarp0) {
+    } else if (warp >= kDrainWarp0 && warp < kDrainWarp0 + 4 * kDrainGroups) {
         // ===================== drain warpgroups: TMEM accumulators -> exact fp32 contraction results =========
         // warpgroup dw owns columns [dw * kNd, (dw + 1) * kNd) of every plane (16 steps of both streams)
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsDrain));
         const int quarter = warp & 3;                          // TMEM lanes this warp may touch
-        const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((warp - 4) >> 2) * kNd;
+        const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((warp - kDrainWarp0) >> 2) * kNd;
         int it = 0;
         uint32_t probe0 = 0;
         PROF_DECL;
@@ -491,8 +495,6 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
         const int pb = u / p.n_tiles, tile = u - pb * p.n_tiles;
         const int n_it = (min(pb * p.pb_size + p.pb_size, p.n_pairs) - pb * p.pb_size) * p.chunks;
         const bool top2 = __ldg(p.npl + tile) > 5;             // plane 5 present
-        const int place = tile * kM + quarter * 32 + lane;
-        const float scale = place < p.P ? p.scale[place] : 0.0f;
         for (int i = 0; i < n_it; ++i, ++it) {
             // X = sum_j P_j 256^j as (xh:xl) for the kNd columns of this lane.  The (pair, 16-column) loads
             // are double-buffered in registers: the tcgen05.ld of step s + 1 is in flight while step s is
@@ -526,7 +528,7 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
                     if (lane == 0) {
                         mbar_arrive(acc_empty + g);
                         // all MMAs of this tile have retired: its spike tile may be overwritten by the TMA
-                        if (g == 2 && warp == 4) mbar_arrive(b_empty + (uint32_t)it % kStages);
+                        if (g == 2 && warp == kDrainWarp0) mbar_arrive(b_empty + (uint32_t)it % kStages);
                     }
                 }
                 if (s + 1 < kSteps) {
@@ -564,7 +566,8 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
                     }
                 }
             }
-            // one rounding to fp32 (cvt.rn.f32.s64), exact power-of-two scale, hand over through TMEM
+            // one rounding to fp32 (cvt.rn.f32.s64), hand over through TMEM; the exact power-of-two scale of the
+            // row is applied by the scan's first operation (an FMA whose product is exact)
             PROF(1);
             mbar_wait_probed(probe, x_empty + xb, ((it >> 1) & 1) ^ 1);
             tc_fence_after();
@@ -577,7 +580,7 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
 #pragma unroll
                 for (int n = 0; n < 16; ++n) {
                     const int m = h * 16 + n;
-                    xf[n] = __fmul_rn(__ll2float_rn((int64_t)(((uint64_t)(uint32_t)xh[m] << 32) | (uint32_t)xl[m])), scale);
+                    xf[n] = __ll2float_rn((int64_t)(((uint64_t)(uint32_t)xh[m] << 32) | (uint32_t)xl[m]));
                 }
                 tmem_st16(tlane + kXCol + xb * kN + h * 16, xf);
             }
@@ -589,7 +592,7 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
             GANTT(24);
         }
         }
-        if (warp == 4) PROF_FLUSH(6);
+        if (warp == kDrainWarp0) PROF_FLUSH(6);
     } else {
         // ===================== scan warpgroup: IAF recurrence of both streams, spike counts ================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsScan));
@@ -606,6 +609,7 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
         const int pr0 = pb * p.pb_size, pr1 = min(pr0 + p.pb_size, p.n_pairs);
         const int place = tile * kM + quarter * 32 + lane;
         const bool live_place = place < p.P;
+        const float scale = live_place ? p.scale[place] : 0.0f;
         for (int pr = pr0; pr < pr1; ++pr) {
             const int b0 = 2 * pr, b1 = 2 * pr + 1;
             const bool live0 = live_place && b0 < p.nb, live1 = live_place && b1 < p.nb;
@@ -623,13 +627,9 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
                 PROF(0);
                 GANTT(33);
 #pragma unroll
-                for (int h = 0; h < kN / 16; ++h) {
-                    float t16[16];
-                    tmem_ld16f(tlane + kXCol + xb * kN + h * 16, t16);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int n = 0; n < 16; ++n) x[h * 16 + n] = t16[n];
-                }
+                for (int h = 0; h < kN / 16; ++h)
+                    tmem_ld16f(tlane + kXCol + xb * kN + h * 16, reinterpret_cast<float(&)[16]>(x[h * 16]));
+                tmem_ld_wait();                                  // all four loads in flight together
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(x_empty + xb);
@@ -657,13 +657,13 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
                     const float2 saved = v;
                     float amax = -1.0f;
                     if (kHidden) {
-                        if (nvalid == kTileSteps) scan_tile_hidden<false>(x, nvalid, v, amax, stage_out);
-                        else scan_tile_hidden<true>(x, nvalid, v, amax, stage_out);
+                        if (nvalid == kTileSteps) scan_tile_hidden<false>(x, scale, nvalid, v, amax, stage_out);
+                        else scan_tile_hidden<true>(x, scale, nvalid, v, amax, stage_out);
                         redo = amax >= 128.0f;                       // beyond LENS_MAX_SPIKE: generic path
                     } else {
                         float2 csum = make_float2(0.0f, 0.0f);
-                        if (nvalid == kTileSteps) scan_tile_unit<false>(x, nvalid, v, csum, amax);
-                        else scan_tile_unit<true>(x, nvalid, v, csum, amax);
+                        if (nvalid == kTileSteps) scan_tile_unit<false>(x, scale, nvalid, v, csum, amax);
+                        else scan_tile_unit<true>(x, scale, nvalid, v, csum, amax);
                         redo = amax >= 2.0f;                         // several spikes in one step
                         if (!redo) {
                             count.x += (float)nvalid - csum.x;       // small integers: exact
@@ -683,7 +683,7 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
 #pragma unroll
                             for (int n = 0; n < kTileSteps; ++n) {
                                 if (n < nvalid) {
-                                    float s = iaf_out<kUnitThr>(vv, x[2 * n + sp], thr, vmin);
+                                    float s = iaf_out<kUnitThr>(vv, __fmul_rn(x[2 * n + sp], scale), thr, vmin);
                                     if (kHidden) {
                                         if (s > (float)LENS_MAX_SPIKE) { s = (float)LENS_MAX_SPIKE; if (live) ++n_over; }
                                         stage_out[(2 * n + sp) * 16] = (uint8_t)s;

@@ -6,7 +6,10 @@
 
 Streams are sharded across ranks; the all-reduced Recall@N counters and the gathered spike counts
 must equal what one rank computes alone for the whole batch.  Also exercises the all-gather of a
-row-sharded place database (config 5 of BASELINE.json) before the network is built.
+row-sharded place database (config 5 of BASELINE.json) before the network is built, and the
+place-sharded mode (every rank ranks its own places for all streams, NCCL all-gather of the per-rank
+top-N lists, lens_topn_merge): the merged lists must equal the single-rank lists bit for bit.
+Also run by tests/test_gpu_multi.py (pytest -m gpu) when the box has >= 2 GPUs.
 """
 import os
 import sys
@@ -16,7 +19,7 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from lens_b200 import synth  # noqa: E402
-from lens_b200.pipeline import InferencePipeline, shard_range  # noqa: E402
+from lens_b200.pipeline import InferencePipeline, PlaceShardedPipeline, shard_range  # noqa: E402
 
 
 def main():
@@ -44,17 +47,23 @@ def main():
                 for r in range(world)]
     dist.all_gather(gathered, out["S"])
     S_all = torch.cat(gathered)
+    # place-sharded mode: all streams on every rank, the database split
+    psp = PlaceShardedPipeline(torch.from_numpy(Wf), full, roi=80, k=8, T=250, L=L, max_streams=B, device=dev)
+    pout = psp.step(frames=torch.from_numpy(frames).to(dev), gt_center=torch.from_numpy(gt).to(dev), gt_tol=2)
     ok = True
     if rank == 0:
         solo = InferencePipeline(torch.from_numpy(Wf), torch.from_numpy(Wo), roi=80, k=8, T=250, L=L,
                                  max_streams=B, device=dev)
         ref = solo.step(frames=torch.from_numpy(frames).to(dev), gt_center=torch.from_numpy(gt).to(dev),
                         gt_tol=2, reduce=False)
-        ok = torch.equal(S_all, ref["S"]) and torch.equal(out["hits"], ref["hits"]) and \
+        ok_streams = torch.equal(S_all, ref["S"]) and torch.equal(out["hits"], ref["hits"]) and \
             torch.equal(out["n_valid"], ref["n_valid"])
+        ok_places = torch.equal(pout["top_idx"], ref["top_idx"]) and torch.equal(pout["top_val"], ref["top_val"]) and \
+            torch.equal(pout["hits"], ref["hits"])
+        ok = ok_streams and ok_places
         print(f"multi_gpu_check world={world}: counts equal={torch.equal(S_all, ref['S'])} "
-              f"hits {out['hits'].tolist()} vs {ref['hits'].tolist()} valid {int(out['n_valid'])} -> "
-              f"{'OK' if ok else 'MISMATCH'}")
+              f"hits {out['hits'].tolist()} vs {ref['hits'].tolist()} valid {int(out['n_valid'])}; "
+              f"place-sharded top-N merge equal={ok_places} -> {'OK' if ok else 'MISMATCH'}")
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

@@ -23,6 +23,26 @@ def test_shard_range_partitions_everything():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_place_shard_range_covers_every_diagonal():
+    """Database sharding: the rows [p0, p1) of all ranks partition the P - L + 1 sequence-matched rows, and
+    with the L - 1 halo places each rank can form every diagonal that starts in its range."""
+    from lens_b200.pipeline import place_shard_range
+    from oracle import oracle as O
+    rng = np.random.default_rng(3)
+    for P, L, world in [(40, 2, 2), (41, 10, 3), (100, 1, 8), (64, 4, 1)]:
+        S = rng.poisson(1.3, (L + 3, P)).astype(np.float32)
+        D = O.seqmatch(S, L)                                   # [P - L + 1, Q - L + 1]
+        rows = []
+        for r in range(world):
+            p0, p1, p1h = place_shard_range(P, L, r, world)
+            assert p1h - p0 >= (p1 - p0) and p1h <= P
+            if p1 > p0:
+                Dr = O.seqmatch(S[:, p0:p1h], L)               # the shard's own matrix
+                assert Dr.shape[0] == p1 - p0
+                rows.append(Dr)
+        assert np.array_equal(np.concatenate(rows), D)
+
+
 def _worker(rank, world, port, B, Q, P, L, tmp):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
