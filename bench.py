@@ -429,7 +429,11 @@ def measure_snn(ctx, c, steps, warmup, W_out_sharded=False, want_e2e=True):
     value = world * units_per_step * steps / (tot_ms / 1e3)
     region_s = sum(ms) / 1e3
     tpeak, tsrc = tensor_peak(peaks, region_s)
-    wl = "streams=%d,queries=%d,places=%d,feature=%d" % (B, Q, P, F)
+    # one launch covers at most `group` streams (the hidden-spike scratch is bounded to 6 GiB, csrc/snn.cu): the
+    # committed ncu traffic figures are per launch of a full group
+    chunks = Q * (-(-T_STEPS // 32))
+    group = 2 * ((6 << 30) // (chunks * 64 * (-(-F // 32) * 32)))
+    wl = "streams=%d,queries=%d,places=%d,feature=%d" % (min(B, group), Q, P, F)
 
     # ---- per-kernel rooflines (CUDA events on the launch stream, recorded by the library / the pipeline)
     def tensor_roof(kernel, flops_per_unit, total_ms, n_launch, traffic_key, algorithmic):

@@ -65,6 +65,13 @@ int lens_bin_events(const uint32_t *t_us, const uint16_t *x, const uint16_t *y, 
                     int index_shift, int wrap_u8, uint8_t *frames, uint8_t *pooled,
                     int32_t *win_events, int64_t *win_offsets, int64_t n_win, void *stream);
 
+/* Precondition of lens_bin_events: t_us ascending (the window ranges are found by binary search, like the
+ * reference's drain-every-timebin loop sees the events in arrival order, lens/collect_data.py:186-191).
+ * Sets *unsorted (device int) to 1 if some t_us[i+1] < t_us[i], else 0.  One streaming pass over t_us
+ * (4 B/event), therefore separate from the binning call; lens_b200.ops.bin_events(check_sorted=True)
+ * runs it and raises.                                                                                  */
+int lens_check_sorted_u32(const uint32_t *t_us, int64_t n, int *unsorted, void *stream);
+
 /* Pooling alone (frames already exist, e.g. decoded PNGs):
  * frames [n][roi][roi] u8 -> pooled [n][dims*dims] u8.  lens/run_model.py:130-137. */
 int lens_pool_frames(const uint8_t *frames, int64_t n, int roi, int k, uint8_t *pooled,

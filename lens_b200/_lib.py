@@ -29,6 +29,7 @@ def _declare(L):
         "lens_bin_events": (i32, [vp, vp, vp, i64, u32, u32, i32, i32, i32, i32, i32, i32,
                                   vp, vp, vp, vp, i64, vp]),
         "lens_pool_frames": (i32, [vp, i64, i32, i32, vp, vp]),
+        "lens_check_sorted_u32": (i32, [vp, i64, vp, vp]),
         "lens_snn_create": (i32, [i32, i32, i32, i32, f32, f32, vp, vp, vp, i32,
                                   C.POINTER(vp), pi64, vp]),
         "lens_snn_destroy": (i32, [vp]),

@@ -13,6 +13,8 @@
 // time array is never touched again.
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace lens {
 
 __global__ void window_offsets_kernel(const uint32_t *__restrict__ t_us, int64_t n_events,
@@ -29,6 +31,23 @@ __global__ void window_offsets_kernel(const uint32_t *__restrict__ t_us, int64_t
         else hi = mid;
     }
     win_offsets[w] = lo;
+}
+
+// Precondition check of lens_bin_events: the window ranges come from a binary search on t_us, which is
+// only meaningful for ascending timestamps.  16-byte loads, grid-stride; *unsorted is set to 1 on a descent.
+__global__ void __launch_bounds__(256) sorted_check_u32_kernel(const uint32_t *__restrict__ t, int64_t n,
+                                                               int *__restrict__ unsorted)
+{
+    const int64_t n4 = n >> 2;
+    bool bad = false;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(t) + i);
+        bad |= v.y < v.x || v.z < v.y || v.w < v.z;
+        if (4 * i + 4 < n) bad |= __ldg(t + 4 * i + 4) < v.w;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (int64_t i = n4 << 2; i + 1 < n; ++i) bad |= t[i + 1] < t[i];
+    if (bad) *unsorted = 1;
 }
 
 struct BinParams {
@@ -279,6 +298,21 @@ extern "C" int lens_bin_events(const uint32_t *t_us, const uint16_t *x, const ui
         bin_kernel<<<grid, 512, smem, st>>>(p);
     }
     LENS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int lens_check_sorted_u32(const uint32_t *t_us, int64_t n, int *unsorted, void *stream)
+{
+    LENS_CHECK_ARG(n >= 0 && unsorted, "lens_check_sorted_u32: bad argument");
+    LENS_CHECK_ARG(n == 0 || t_us, "lens_check_sorted_u32: NULL array");
+    LENS_CHECK_ARG(((uintptr_t)t_us & 15) == 0, "lens_check_sorted_u32: t_us must be 16-byte aligned");
+    cudaStream_t st = as_stream(stream);
+    LENS_CUDA(cudaMemsetAsync(unsorted, 0, sizeof(int), st));
+    if (n > 1) {
+        const int64_t blocks = std::min<int64_t>(ceil_div64(n >> 2, 256) + 1, (int64_t)std::max(sm_count(), 1) * 16);
+        sorted_check_u32_kernel<<<(unsigned)blocks, 256, 0, st>>>(t_us, n, unsorted);
+        LENS_LAUNCH_CHECK();
+    }
     return 0;
 }
 

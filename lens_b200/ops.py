@@ -35,17 +35,24 @@ def pool_frames(frames, k):
 
 
 def bin_events(t_us, x, y, t0_us, window_us, n_win, roi, k, roi_x0=0, roi_y0=0, index_shift=1,
-               wrap_u8=True, want_frames=True, want_pooled=True):
+               wrap_u8=True, want_frames=True, want_pooled=True, check_sorted=False):
     """Event stream -> (frames u8 [n_win, roi, roi], pooled u8 [n_win, I], events-per-window i32).
 
     Mirrors lens/collect_data.py:186-202 (`frame[y-1, x-1] += 1`, `.astype(np.uint8)`); the
     caller drops windows whose count is 0 to reproduce create_images' "No events" branch.
+    t_us must be ascending (window ranges are found by binary search); check_sorted=True verifies it with
+    one extra pass over t_us (lens_check_sorted_u32, synchronises) and raises ValueError otherwise.
     """
     require_cuda(t_us, x, y)
     assert t_us.dtype == torch.int32 or t_us.dtype == torch.uint32
     assert x.dtype in (torch.int16, torch.uint16) and y.dtype in (torch.int16, torch.uint16)
     n = t_us.numel()
     dev = t_us.device
+    if check_sorted:
+        flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        check(_lib.lib().lens_check_sorted_u32(ptr(t_us), n, ptr(flag), stream_ptr()), "lens_check_sorted_u32")
+        if int(flag.item()):
+            raise ValueError("event timestamps must be ascending")
     dims, _ = pool_geometry(roi, k)
     frames = torch.empty((n_win, roi, roi), dtype=torch.uint8, device=dev) if want_frames else None
     pooled = torch.empty((n_win, dims * dims), dtype=torch.uint8, device=dev) if want_pooled else None

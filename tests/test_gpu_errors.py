@@ -2,6 +2,7 @@
 (LensError in the Python layer), never as a crash, and leave the library usable."""
 import ctypes as C
 
+import numpy as np
 import pytest
 import torch
 
@@ -63,3 +64,22 @@ def test_bad_arguments_are_reported_not_fatal():
     # ... and the library still works afterwards
     out = net.run_streams(pooled=torch.full((2, 1, 100), 200, dtype=torch.uint8, device="cuda"))
     assert out.shape == (2, 1, 64) and torch.isfinite(out).all()
+
+
+def test_bin_events_sortedness_check():
+    """lens_bin_events needs ascending timestamps (binary-searched windows); the optional check finds a
+    single descent anywhere in the array (vector body, tail, across the 16-byte seams)."""
+    from lens_b200 import ops
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 5, 64, 1001, 4096 + 3):
+        t = np.sort(rng.integers(0, 5000, n)).astype(np.int32)
+        x = rng.integers(0, 16, n).astype(np.int16)
+        args = (torch.from_numpy(x).cuda(), torch.from_numpy(x).cuda(), 0, 1000, 5, 16, 2)
+        ops.bin_events(torch.from_numpy(t).cuda(), *args, check_sorted=True)          # sorted: fine
+        for pos in sorted({0, n // 2, n - 2, min(3, n - 2), min(4, n - 2)}):
+            if pos < 0 or pos + 1 >= n or t[pos] == t[-1] + 7:
+                continue
+            bad = t.copy()
+            bad[pos] = t[-1] + 7                                                         # a descent after pos
+            with pytest.raises(ValueError, match="ascending"):
+                ops.bin_events(torch.from_numpy(bad).cuda(), *args, check_sorted=True)
