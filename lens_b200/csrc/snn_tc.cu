@@ -226,10 +226,10 @@ struct Params {
 };
 
 #ifdef LENS_TC_PROFILE
-#define PROF_DECL long long prof_t = clock64(), prof_acc[6] = {0, 0, 0, 0, 0, 0}
+#define PROF_DECL long long prof_t = clock64(), prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
 #define PROF(i) do { const long long now_ = clock64(); prof_acc[i] += now_ - prof_t; prof_t = now_; } while (0)
 #define GANTT(k) do { if (blockIdx.x == 0 && lane == 0 && (int)it >= 1000 && (int)it < 1003) p.prof[1024 * 24 + ((int)it - 1000) * 48 + (k)] = clock64(); } while (0)
-#define PROF_FLUSH(base) do { if (lane == 0) for (int i_ = 0; i_ < 6; ++i_) p.prof[blockIdx.x * 24 + (base) + i_] = prof_acc[i_]; } while (0)
+#define PROF_FLUSH(base) do { if (lane == 0) for (int i_ = 0; i_ < 8; ++i_) p.prof[blockIdx.x * 24 + (base) + i_] = prof_acc[i_]; } while (0)
 #else
 #define PROF_DECL
 #define PROF(i)
@@ -519,7 +519,9 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
 #pragma unroll
             for (int s = 0; s < kSteps; ++s) {
                 const int g = s / kH, h = s % kH;
+                PROF(1);
                 tmem_ld_wait();                                  // buf[s & 1] has landed
+                PROF(5);
                 if (h == kH - 1) {
                     // every load of pair g is complete: hand the pair back to its MMA warp
                     tc_fence_before();
@@ -536,9 +538,8 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
                     if (h2 == 0) {
                         PROF(1);
                         mbar_wait_probed(g2 == 1 ? probe1 : probe2, acc_full + g2, it & 1);
-                        PROF(4);
                         tc_fence_after();
-                        PROF(5);
+                        PROF(4);
                         GANTT(17 + 2 * g2);
                     }
                     tmem_ld16(tlane + (2 * g2) * kN + h2 * 16, reinterpret_cast<int32_t(&)[16]>(buf[(s + 1) & 1][0]));
@@ -582,9 +583,11 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
                     const int m = h * 16 + n;
                     xf[n] = __ll2float_rn((int64_t)(((uint64_t)(uint32_t)xh[m] << 32) | (uint32_t)xl[m]));
                 }
+                PROF(6);
                 tmem_st16(tlane + kXCol + xb * kN + h * 16, xf);
             }
             tmem_st_wait();
+            PROF(7);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(x_full + xb);
@@ -592,7 +595,7 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
             GANTT(24);
         }
         }
-        if (warp == kDrainWarp0) PROF_FLUSH(6);
+        if (warp == kDrainWarp0) PROF_FLUSH(8);
     } else {
         // ===================== scan warpgroup: IAF recurrence of both streams, spike counts ================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsScan));
@@ -728,7 +731,7 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
             if (live1) p.v2[(size_t)b1 * p.P + place] = v.y;
         }
         }
-        if (warp == kScanWarp0) PROF_FLUSH(12);
+        if (warp == kScanWarp0) PROF_FLUSH(16);
         if (kHidden) {
             if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
             if (n_over) atomicAdd((unsigned long long *)p.overflow, (unsigned long long)n_over);
@@ -935,13 +938,14 @@ struct ProfDump {
         std::vector<long long> hbuf(n * 24);
         cudaStreamSynchronize(st);
         cudaMemcpy(hbuf.data(), d, hbuf.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-        double avg[18] = {0};
-        for (unsigned b = 0; b < n; ++b) for (int i = 0; i < 18; ++i) avg[i] += (double)hbuf[b * 24 + i] / n / iters;
+        double avg[24] = {0};
+        for (unsigned b = 0; b < n; ++b) for (int i = 0; i < 24; ++i) avg[i] += (double)hbuf[b * 24 + i] / n / iters;
         fprintf(stderr, "[tc-prof %s] clk per tile-iteration (avg over %u CTAs, %lld iters/CTA)\n", name, n, iters);
         fprintf(stderr, "  mma  : planes-wait %.0f  b_full-wait %.0f  acc_empty-wait %.0f  issue %.0f\n", avg[0], avg[1], avg[2], avg[3]);
-        fprintf(stderr, "  drain: acc_full-wait %.0f  fold %.0f  x_empty-wait %.0f  convert+st %.0f  pair 1/2 wait %.0f  fence %.0f\n",
-                avg[6], avg[7], avg[8], avg[9], avg[10], avg[11]);
-        fprintf(stderr, "  scan : x_full-wait %.0f  other %.0f  load %.0f  chain %.0f\n", avg[12], avg[13], avg[14], avg[15]);
+        fprintf(stderr, "  drain: acc_full-wait %.0f  fold %.0f  x_empty-wait %.0f  fence+arrive %.0f  pair 1/2 wait %.0f  tcgen05.wait::ld %.0f\n",
+                avg[8], avg[9], avg[10], avg[11], avg[12], avg[13]);
+        fprintf(stderr, "  drain: conversions %.0f  tcgen05.st + wait::st %.0f\n", avg[14], avg[15]);
+        fprintf(stderr, "  scan : x_full-wait %.0f  other %.0f  load %.0f  chain %.0f\n", avg[16], avg[17], avg[18], avg[19]);
         long long g_[144];
         cudaMemcpy(g_, d + 1024 * 24, sizeof(g_), cudaMemcpyDeviceToHost);
         const long long t0_ = g_[0];
