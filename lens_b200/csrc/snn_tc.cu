@@ -322,6 +322,38 @@ __device__ __forceinline__ void scan_tile_hidden(const float (&x)[kN], float sca
     }
 }
 
+// The hidden-layer scan for TWO stream pairs at once (tiles of pairs A and B that cover the same chunk): the scan
+// warp then advances two independent packed chains, which hides the latency of the 7-operation chain step that a
+// single pair leaves exposed (the recurrence is serial in time, so the parallelism has to come from streams).
+// One call covers 16 steps: xa / xb = 32 exchange columns of A / B (column 2n + s = step n0 + n of stream s).
+template <bool kRagged>
+__device__ __forceinline__ void scan_half2_hidden(const float (&xa)[32], const float (&xb)[32], float scale, int n0,
+                                                  int nvalid, float2 &va, float2 &vb, float &amax, uint8_t *out_a,
+                                                  uint8_t *out_b)
+{
+    const float2 m1 = make_float2(-1.0f, -1.0f), big = make_float2(8388608.0f, 8388608.0f);
+    const float2 big1 = make_float2(8388609.0f, 8388609.0f), sc = make_float2(scale, scale);
+#pragma unroll
+    for (int n = 0; n < kTileSteps / 2; ++n) {
+        if (!kRagged || n0 + n < nvalid) {
+            const float2 a = __ffma2_rn(make_float2(xa[2 * n], xa[2 * n + 1]), sc, va);
+            const float2 b = __ffma2_rn(make_float2(xb[2 * n], xb[2 * n + 1]), sc, vb);
+            const float2 ta = __fadd2_rz(make_float2(fmaxf(a.x, 0.0f), fmaxf(a.y, 0.0f)), big);
+            const float2 tb = __fadd2_rz(make_float2(fmaxf(b.x, 0.0f), fmaxf(b.y, 0.0f)), big);
+            amax = fmax3(fmax3(amax, a.x, a.y), b.x, b.y);
+            const float2 ra = __fadd2_rn(a, __ffma2_rn(ta, m1, big1));
+            const float2 rb = __fadd2_rn(b, __ffma2_rn(tb, m1, big1));
+            va = __fadd2_rn(make_float2(fmaxf(ra.x, 0.0f), fmaxf(ra.y, 0.0f)), m1);
+            vb = __fadd2_rn(make_float2(fmaxf(rb.x, 0.0f), fmaxf(rb.y, 0.0f)), m1);
+            const int row = 2 * (n0 + n);
+            out_a[row * 16] = (uint8_t)__float_as_uint(ta.x);
+            out_a[(row + 1) * 16] = (uint8_t)__float_as_uint(ta.y);
+            out_b[row * 16] = (uint8_t)__float_as_uint(tb.x);
+            out_b[(row + 1) * 16] = (uint8_t)__float_as_uint(tb.y);
+        }
+    }
+}
+
 // kKSteps = Fp / 32 as a compile-time constant (0 = generic runtime loop): with it the MMAs of a tile
 // are straight-line code whose descriptors are constant offsets from two uniform bases.
 // kHidden: feature layer (IAF#1) instead of output layer (IAF#2): spikes leave as pair tiles, no counts.
@@ -347,6 +379,12 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
     uint8_t *sOut = reinterpret_cast<uint8_t *>(bars) + 256;  // [2][8][64][16] spike staging (kHidden only)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // The hidden layer takes the stream pairs of a block two at a time with their chunks interleaved (A0 B0 A1 B1 ...)
+    // and scans the two tiles of a chunk together: its IAF#1 chain is 7 dependent operations per step and the scan
+    // warpgroup is what bounds that kernel, so two independent chains per thread pay.  The output layer does not:
+    // there the drain warpgroups bound the tile and a faster, burstier scan only takes issue slots from them
+    // (measured: -7 %, profiles/r02_tc_phase_profile.md).
+    constexpr int kPairStep = kHidden ? 2 : 1;
     // Work = super-items (pair block, place tile), tile fastest, dealt round-robin to the persistent CTAs:
     // the CTAs running at the same time work on the same few pair blocks with different place tiles, so a
     // hidden-spike tile is fetched from HBM once and then served from L2 to the other place tiles; a CTA
@@ -395,16 +433,19 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
                     bulk_g2s(sA + o, src + o, plane_bytes, a_full);
             }
             __syncwarp();
-            for (int pr = pr0; pr < pr1; ++pr) {
-                const int8_t *sb = p.S1 + (size_t)pr * p.chunks * tile_bytes;
-                for (int c = 0; c < p.chunks; ++c, ++it) {
-                    const uint32_t stage = it % kStages, phase = (it / kStages) & 1;
-                    mbar_wait(b_empty + stage, phase ^ 1);
-                    if (elect_one()) {
-                        mbar_expect_tx(b_full + stage, tile_bytes);
-                        bulk_g2s(sB + stage * tile_bytes, sb + (size_t)c * tile_bytes, tile_bytes, b_full + stage);
+            for (int pa = pr0; pa < pr1; pa += kPairStep) {
+                const int npair = min(kPairStep, pr1 - pa);
+                for (int c = 0; c < p.chunks; ++c) {
+                    for (int j = 0; j < npair; ++j, ++it) {
+                        const int8_t *src = p.S1 + ((size_t)(pa + j) * p.chunks + c) * tile_bytes;
+                        const uint32_t stage = it % kStages, phase = (it / kStages) & 1;
+                        mbar_wait(b_empty + stage, phase ^ 1);
+                        if (elect_one()) {
+                            mbar_expect_tx(b_full + stage, tile_bytes);
+                            bulk_g2s(sB + stage * tile_bytes, src, tile_bytes, b_full + stage);
+                        }
+                        __syncwarp();
                     }
-                    __syncwarp();
                 }
             }
         }
@@ -597,16 +638,200 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
         }
         if (warp == kDrainWarp0) PROF_FLUSH(8);
     } else {
-        // ===================== scan warpgroup: IAF recurrence of both streams, spike counts ================
+        // ===================== scan warpgroup: IAF recurrence of the streams, spikes out ===================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsScan));
         const int quarter = warp & 3;
         const float thr = p.thr, vmin = p.vmin;
-        const int Q = p.steps / p.T;
         const int cpq = chunks_per_query(p.T);
         const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        long long n_over = 0;
+        constexpr bool kFast = kUnitThr && !kDebug;
         int it = 0;
         PROF_DECL;
+        if (kHidden) {
+        // ---- hidden layer (IAF#1): spike bytes leave as pair tiles for the output layer.  Tiles arrive
+        // chunk-interleaved from two independent stream pairs A and B (kPairStep); on the fast path the two tiles of
+        // a chunk are scanned TOGETHER, 16 steps at a time, as two independent packed chains.  A block's odd last
+        // pair, debug output and a half tile in which a step left the fast path's domain go tile by tile / step by step.
+        long long n_over = 0;
+        for (int u = blockIdx.x; u < p.n_super; u += gridDim.x) {
+        const int pb = u / p.n_tiles, tile = u - pb * p.n_tiles;
+        const int pr0 = pb * p.pb_size, pr1 = min(pr0 + p.pb_size, p.n_pairs);
+        const int place = tile * kM + quarter * 32 + lane;
+        const bool live_place = place < p.P;
+        const float scale = live_place ? p.scale[place] : 0.0f;
+        // a finished tile: generic-proxy writes -> async proxy, then one lane ships the warp's two k-chunks
+        // (contiguous in the pair-tile layout) with one bulk store
+        auto ship = [&](int pr, int c, int itx) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+                const int kcw = tile * 8 + quarter * 2, nkc = min(2, p.out_Fp / 16 - kcw);
+                if (nkc > 0)
+                    bulk_s2g(p.S1_out + ((size_t)pr * p.chunks + c) * ((size_t)kN * p.out_Fp) + (size_t)kcw * 1024,
+                             sOut + (itx & 1) * 8192 + quarter * 2048, (uint32_t)nkc * 1024u);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        };
+        for (int pa = pr0; pa < pr1; pa += kPairStep) {
+            const int npair = min(kPairStep, pr1 - pa);
+            // state of the (up to) two pairs: index 0 = pair A, 1 = pair B; .x = even stream, .y = odd stream
+            float2 v[2];
+            bool live[2][2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int b0 = 2 * (pa + j), b1 = b0 + 1;
+                live[j][0] = live_place && j < npair && b0 < p.nb;
+                live[j][1] = live_place && j < npair && b1 < p.nb;
+                v[j] = make_float2(live[j][0] ? p.v2[(size_t)b0 * p.P + place] : 0.0f,
+                                   live[j][1] ? p.v2[(size_t)b1 * p.P + place] : 0.0f);
+            }
+            int cq = 0, q = 0;                                   // chunk within the query, query index
+            for (int c = 0; c < p.chunks; ++c) {
+                // this chunk: steps [t_base, t_base + nvalid) of query q (chunks never straddle a query)
+                const int t_base = q * p.T + cq * kTileSteps;
+                const int nvalid = min(kTileSteps, min(p.T - cq * kTileSteps, p.steps - t_base));
+                if (++cq == cpq) { cq = 0; ++q; }
+                if (kFast && npair == 2) {
+                    // ---------------- two tiles together ----------------
+                    const int ita = it, itb = it + 1;
+                    it += 2;
+                    const uint32_t xa_col = tlane + kXCol + (uint32_t)(ita & 1) * kN, xb_col = tlane + kXCol + (uint32_t)(itb & 1) * kN;
+                    // staging tiles [kc][row = 2n + stream][16] of A and B
+                    uint8_t *out_a = sOut + (ita & 1) * 8192 + (quarter * 2 + (lane >> 4)) * 1024 + (lane & 15);
+                    uint8_t *out_b = sOut + (itb & 1) * 8192 + (quarter * 2 + (lane >> 4)) * 1024 + (lane & 15);
+                    PROF(1);
+                    mbar_wait(x_full + (ita & 1), (ita >> 1) & 1);
+                    mbar_wait(x_full + (itb & 1), (itb >> 1) & 1);
+                    tc_fence_after();
+                    PROF(0);
+                    // both staging buffers are rewritten: this warp's two stores of the previous chunk must have been read
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    __syncwarp();
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        float xa[32], xb[32];
+                        tmem_ld16f(xa_col + half * 32, reinterpret_cast<float(&)[16]>(xa[0]));
+                        tmem_ld16f(xa_col + half * 32 + 16, reinterpret_cast<float(&)[16]>(xa[16]));
+                        tmem_ld16f(xb_col + half * 32, reinterpret_cast<float(&)[16]>(xb[0]));
+                        tmem_ld16f(xb_col + half * 32 + 16, reinterpret_cast<float(&)[16]>(xb[16]));
+                        tmem_ld_wait();
+                        if (half == 1) {
+                            // every column of both tiles is in registers: hand the exchange buffers back
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) { mbar_arrive(x_empty + (ita & 1)); mbar_arrive(x_empty + (itb & 1)); }
+                        }
+                        PROF(2);
+                        const int n0 = half * (kTileSteps / 2);
+                        if (n0 < nvalid) {
+                            const float2 sva = v[0], svb = v[1];
+                            float amax = -1.0f;
+                            if (nvalid >= n0 + kTileSteps / 2) scan_half2_hidden<false>(xa, xb, scale, n0, nvalid, v[0], v[1], amax, out_a, out_b);
+                            else scan_half2_hidden<true>(xa, xb, scale, n0, nvalid, v[0], v[1], amax, out_a, out_b);
+                            if (amax >= 128.0f) {
+                                // beyond LENS_MAX_SPIKE somewhere in these 16 steps: redo them one by one (clipped, counted)
+                                v[0] = sva; v[1] = svb;
+#pragma unroll
+                                for (int j = 0; j < 2; ++j) {
+#pragma unroll
+                                    for (int sp = 0; sp < 2; ++sp) {
+                                        float vv = sp ? v[j].y : v[j].x;
+                                        uint8_t *out = j ? out_b : out_a;
+#pragma unroll
+                                        for (int n = 0; n < kTileSteps / 2; ++n) {
+                                            if (n0 + n < nvalid) {
+                                                float sk = iaf_out<kUnitThr>(vv, __fmul_rn(j ? xb[2 * n + sp] : xa[2 * n + sp], scale), thr, vmin);
+                                                if (sk > (float)LENS_MAX_SPIKE) { sk = (float)LENS_MAX_SPIKE; if (live[j][sp]) ++n_over; }
+                                                out[(2 * (n0 + n) + sp) * 16] = (uint8_t)sk;
+                                            }
+                                        }
+                                        if (sp) v[j].y = vv; else v[j].x = vv;
+                                    }
+                                }
+                            }
+                        }
+                        PROF(3);
+                    }
+                    for (int n = nvalid; n < kTileSteps; ++n) {            // rows of a ragged chunk that hold no step
+                        out_a[(2 * n) * 16] = 0; out_a[(2 * n + 1) * 16] = 0;
+                        out_b[(2 * n) * 16] = 0; out_b[(2 * n + 1) * 16] = 0;
+                    }
+                    ship(pa, c, ita);
+                    ship(pa + 1, c, itb);
+                } else {
+                    // ---------------- tile by tile ----------------
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        if (j >= npair) break;
+                        const int pr = pa + j;
+                        const uint32_t xb = it & 1;
+                        float x[kN];
+                        PROF(1);
+                        mbar_wait(x_full + xb, (it >> 1) & 1);
+                        tc_fence_after();
+                        PROF(0);
+#pragma unroll
+                        for (int h = 0; h < kN / 16; ++h)
+                            tmem_ld16f(tlane + kXCol + xb * kN + h * 16, reinterpret_cast<float(&)[16]>(x[h * 16]));
+                        tmem_ld_wait();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(x_empty + xb);
+                        PROF(2);
+                        const int itx = it;
+                        ++it;
+                        uint8_t *stage_out = sOut + (itx & 1) * 8192 + (quarter * 2 + (lane >> 4)) * 1024 + (lane & 15);
+                        // every scan warp ships its own 32 neurons, so the staging buffers need warp-level
+                        // synchronisation only: this warp's store of two tiles ago has been read
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        __syncwarp();
+                        bool redo = true;
+                        if (kFast) {
+                            const float2 saved = v[j];
+                            float amax = -1.0f;
+                            if (nvalid == kTileSteps) scan_tile_hidden<false>(x, scale, nvalid, v[j], amax, stage_out);
+                            else scan_tile_hidden<true>(x, scale, nvalid, v[j], amax, stage_out);
+                            redo = amax >= 128.0f;                       // beyond LENS_MAX_SPIKE: generic path
+                            if (redo) v[j] = saved;
+                        }
+                        if (redo) {
+#pragma unroll
+                            for (int sp = 0; sp < 2; ++sp) {
+                                const bool lv = live[j][sp];
+                                const int b = 2 * pr + sp;
+                                float vv = sp ? v[j].y : v[j].x;
+#pragma unroll
+                                for (int n = 0; n < kTileSteps; ++n) {
+                                    if (n < nvalid) {
+                                        float sk = iaf_out<kUnitThr>(vv, __fmul_rn(x[2 * n + sp], scale), thr, vmin);
+                                        if (sk > (float)LENS_MAX_SPIKE) { sk = (float)LENS_MAX_SPIKE; if (lv) ++n_over; }
+                                        stage_out[(2 * n + sp) * 16] = (uint8_t)sk;
+                                        if (kDebug && lv) p.out_steps[((size_t)b * p.steps + t_base + n) * p.P + place] = (uint8_t)sk;
+                                    }
+                                }
+                                if (sp) v[j].y = vv; else v[j].x = vv;
+                            }
+                        }
+                        PROF(3);
+                        for (int n = nvalid; n < kTileSteps; ++n) { stage_out[(2 * n) * 16] = 0; stage_out[(2 * n + 1) * 16] = 0; }
+                        ship(pr, c, itx);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                if (live[j][0]) p.v2[(size_t)(2 * (pa + j)) * p.P + place] = v[j].x;
+                if (live[j][1]) p.v2[(size_t)(2 * (pa + j) + 1) * p.P + place] = v[j].y;
+            }
+        }
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (n_over) atomicAdd((unsigned long long *)p.overflow, (unsigned long long)n_over);
+        } else {
+        // ---- output layer (IAF#2): spike counts per query = the similarity rows.  One stream pair at a time: here
+        // the drain warpgroups bound the tile, and a scan that runs two pairs together only takes issue slots from
+        // them (measured: -7 %, profiles/r02_tc_phase_profile.md).
+        const int Q = p.steps / p.T;
         for (int u = blockIdx.x; u < p.n_super; u += gridDim.x) {
         const int pb = u / p.n_tiles, tile = u - pb * p.n_tiles;
         const int pr0 = pb * p.pb_size, pr1 = min(pr0 + p.pb_size, p.n_pairs);
@@ -643,37 +868,23 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
                 const int nvalid = min(kTileSteps, min(p.T - cq * kTileSteps, p.steps - t_base));
                 const bool q_done = (cq + 1) * kTileSteps >= p.T;
                 if (++cq == cpq) { cq = 0; }
-                if (!kHidden && !live0 && !live1) { if (q_done) ++q; continue; }
-                // hidden layer: this tile's spike bytes are staged in shared memory [kc][row = 2n + stream][16]
-                uint8_t *stage_out = sOut + (it & 1) * 8192 + (quarter * 2 + (lane >> 4)) * 1024 + (lane & 15);
-                if (kHidden) {
-                    // every scan warp ships its own 32 neurons (two 1 KB k-chunks), so the staging buffers need
-                    // warp-level synchronisation only: this warp's store of two tiles ago has been read
-                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                    __syncwarp();
-                }
-
+                if (!live0 && !live1) { if (q_done) ++q; continue; }
                 bool redo = true;
-                if (kUnitThr && !kDebug) {
-                    // Fast path: both streams as packed f32x2 chains (see scan_tile_*); a tile in which some
-                    // step leaves the fast path's domain is redone step by step below.
+                if (kFast) {
+                    // Fast path: both streams as one packed f32x2 chain (scan_tile_unit); a tile in which some step
+                    // leaves the fast path's domain is redone step by step below.
                     const float2 saved = v;
                     float amax = -1.0f;
-                    if (kHidden) {
-                        if (nvalid == kTileSteps) scan_tile_hidden<false>(x, scale, nvalid, v, amax, stage_out);
-                        else scan_tile_hidden<true>(x, scale, nvalid, v, amax, stage_out);
-                        redo = amax >= 128.0f;                       // beyond LENS_MAX_SPIKE: generic path
+                    float2 csum = make_float2(0.0f, 0.0f);
+                    if (nvalid == kTileSteps) scan_tile_unit<false>(x, scale, nvalid, v, csum, amax);
+                    else scan_tile_unit<true>(x, scale, nvalid, v, csum, amax);
+                    redo = amax >= 2.0f;                         // several spikes in one step
+                    if (!redo) {
+                        count.x += (float)nvalid - csum.x;       // small integers: exact
+                        count.y += (float)nvalid - csum.y;
                     } else {
-                        float2 csum = make_float2(0.0f, 0.0f);
-                        if (nvalid == kTileSteps) scan_tile_unit<false>(x, scale, nvalid, v, csum, amax);
-                        else scan_tile_unit<true>(x, scale, nvalid, v, csum, amax);
-                        redo = amax >= 2.0f;                         // several spikes in one step
-                        if (!redo) {
-                            count.x += (float)nvalid - csum.x;       // small integers: exact
-                            count.y += (float)nvalid - csum.y;
-                        }
+                        v = saved;
                     }
-                    if (redo) v = saved;
                 }
                 // generic: multi-spike steps, debug output, other thresholds
                 if (redo) {
@@ -682,60 +893,37 @@ __global__ void __launch_bounds__(kThreads, 1) output_tc_kernel(Params p)
                         const bool live = sp ? live1 : live0;
                         const int b = sp ? b1 : b0;
                         float vv = sp ? v.y : v.x, cnt = 0.0f;
-                        if (kHidden || live) {
+                        if (live) {
 #pragma unroll
                             for (int n = 0; n < kTileSteps; ++n) {
                                 if (n < nvalid) {
-                                    float s = iaf_out<kUnitThr>(vv, __fmul_rn(x[2 * n + sp], scale), thr, vmin);
-                                    if (kHidden) {
-                                        if (s > (float)LENS_MAX_SPIKE) { s = (float)LENS_MAX_SPIKE; if (live) ++n_over; }
-                                        stage_out[(2 * n + sp) * 16] = (uint8_t)s;
-                                        if (kDebug && live) p.out_steps[((size_t)b * p.steps + t_base + n) * p.P + place] = (uint8_t)s;
-                                    } else {
-                                        if (kDebug) p.out_steps[((size_t)b * p.steps + t_base + n) * p.P + place] = (uint8_t)fminf(s, 255.0f);
-                                        cnt += s;
-                                    }
+                                    const float sk = iaf_out<kUnitThr>(vv, __fmul_rn(x[2 * n + sp], scale), thr, vmin);
+                                    if (kDebug) p.out_steps[((size_t)b * p.steps + t_base + n) * p.P + place] = (uint8_t)fminf(sk, 255.0f);
+                                    cnt += sk;
                                 }
                             }
                         }
                         if (sp) { v.y = vv; count.y += cnt; } else { v.x = vv; count.x += cnt; }
                     }
                 }
-                if (!kHidden && q_done) {
+                if (q_done) {
                     // last chunk of query q: its similarity row entries (lens/run_model.py:239)
                     if (q < Q) {
                         if (live0) p.counts[((size_t)b0 * Q + q) * p.P + place] = count.x;
                         if (live1) p.counts[((size_t)b1 * Q + q) * p.P + place] = count.y;
                     }
                     count = make_float2(0.0f, 0.0f);
+                    ++q;
                 }
-                if (q_done) ++q;
                 PROF(3);
                 GANTT(35);
-                if (kHidden) {
-                    for (int n = nvalid; n < kTileSteps; ++n) { stage_out[(2 * n) * 16] = 0; stage_out[(2 * n + 1) * 16] = 0; }
-                    // generic-proxy writes -> async proxy, then one lane ships the warp's two k-chunks of the
-                    // tile (contiguous in the pair-tile layout) with one bulk store
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) {
-                        const int kcw = tile * 8 + quarter * 2, nkc = min(2, p.out_Fp / 16 - kcw);
-                        if (nkc > 0)
-                            bulk_s2g(p.S1_out + ((size_t)pr * p.chunks + c) * ((size_t)kN * p.out_Fp) + (size_t)kcw * 1024,
-                                     sOut + (it & 1) * 8192 + quarter * 2048, (uint32_t)nkc * 1024u);
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    }
-                }
             }
             if (live0) p.v2[(size_t)b0 * p.P + place] = v.x;
             if (live1) p.v2[(size_t)b1 * p.P + place] = v.y;
         }
         }
-        if (warp == kScanWarp0) PROF_FLUSH(16);
-        if (kHidden) {
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-            if (n_over) atomicAdd((unsigned long long *)p.overflow, (unsigned long long)n_over);
         }
+        if (warp == kScanWarp0) PROF_FLUSH(16);
     }
     tc_fence_before();
     __syncthreads();
@@ -790,7 +978,7 @@ __global__ void fill_int_kernel(int *dst, int n, int value)
 // dealt round-robin to `grid` persistent CTAs.  pb_size balances three things: the makespan (rounds x
 // pb_size pair-items, every pair-item costs the same), the digit-plane reloads (once per super-item), and
 // the L2 footprint of the pair blocks in flight (their spike tiles should be fetched from HBM only once).
-static void schedule(Params &p, int sms, size_t pair_bytes, unsigned &grid)
+static void schedule(Params &p, int sms, size_t pair_bytes, unsigned &grid, int min_m = 1)
 {
     long long cost[17], best_cost = -1;
     for (int m = 1; m <= 16; ++m) {
@@ -807,6 +995,7 @@ static void schedule(Params &p, int sms, size_t pair_bytes, unsigned &grid)
         if (window <= 64.0 * 1024 * 1024) best_m = m;                // largest block whose window fits L2
     }
     if (!best_m) best_m = smallest;
+    if (best_m < min_m) best_m = std::max(1, std::min(min_m, p.n_pairs));   // the hidden layer pairs up stream pairs
     p.pb_size = best_m;
     p.n_super = ceil_div(p.n_pairs, best_m) * p.n_tiles;
     grid = (unsigned)std::min<long long>(sms, p.n_super);
@@ -1031,7 +1220,7 @@ int snn_tc_hidden(SnnHandle *h, const uint8_t *pooled, int nb, int b0, int steps
     p.npl = h->Wf_npl;
     const size_t smem = tc::smem_bytes(h->Ip, true);
     unsigned grid_x = 1;
-    tc::schedule(p, sms, (size_t)chunks * s1_tile_bytes(h->Ip), grid_x);
+    tc::schedule(p, sms, (size_t)chunks * s1_tile_bytes(h->Ip), grid_x, 2);
     dim3 grid(grid_x);
 #ifdef LENS_TC_PROFILE
     ProfDump prof_dump(grid.x, st, (long long)h->F_tiles * p.n_pairs * p.chunks / grid.x, "hidden");
