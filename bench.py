@@ -268,7 +268,7 @@ def run_reference(args):
     cb, ms = cpu_arm(c, seconds=budget, steps=args.steps, warmup=args.warmup)
     line = dict(metric="query_timesteps_per_sec", value=cb["value"], unit="query_timesteps/s",
                 n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=ms,
-                higher_is_better=True, scaling=c["scaling"], vs_baseline=None, dtype="f32+int64", data="synthetic",
+                higher_is_better=True, scaling=c["scaling"], vs_baseline=None, dtype="i8->i64+f32", data="synthetic",
                 impl="reference", config=workload_config(c, world), cpu_baseline=cb,
                 e2e=dict(value=cb["value"], unit="query_timesteps/s", h2d_bytes_per_step=0,
                          d2h_bytes_per_step=0),
@@ -455,7 +455,8 @@ def measure_snn(ctx, c, steps, warmup, W_out_sharded=False, want_e2e=True):
     k4_ach = k4_bytes / (match_ms / 1e3) / 1e9 if match_ms > 0 else 0.0
     k4 = dict(kernel="K4 sequence matching + top-%d + recall counters" % N_TOP, bound="hbm", achieved=k4_ach,
               peak=peaks["hbm_gbs"], unit="GB/s", frac=k4_ach / peaks["hbm_gbs"],
-              traffic=load_traffic("seqmatch_topk_kernel", wl), peak_source=peaks["source"],
+              traffic=load_traffic("seqmatch_topk_kernel", "streams=%d,queries=%d,places=%d,feature=%d" % (B, Q, P, F)),
+              peak_source=peaks["source"],
               ms_per_step=match_ms / steps, share_of_step=match_ms / sum(ms),
               algorithmic="4 B per similarity entry read once + 8 B per top-N entry")
     res.update(value=value, ms_per_step=tot_ms / steps, units_per_step_per_gpu=units_per_step,
@@ -603,13 +604,13 @@ def main():
         lat = measure_latency(ctx, c, reps=max(args.steps, 3))
         line = dict(metric="query_timesteps_per_sec", value=lat["value"], unit="query_timesteps/s", n_gpus=world,
                     steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=lat["ms_per_pass"],
-                    higher_is_better=True, scaling="replicas", vs_baseline=None, dtype="f32+int64",
+                    higher_is_better=True, scaling="replicas", vs_baseline=None, dtype="i8->i64+f32",
                     data="synthetic", config=workload_config(c, world), latency=lat)
     else:
         m = measure_snn(ctx, c, args.steps, args.warmup, W_out_sharded=(c["name"] == "config5"))
         line = dict(metric="query_timesteps_per_sec", value=m.pop("value"), unit="query_timesteps/s", n_gpus=world,
                     steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=m.pop("ms_per_step"),
-                    higher_is_better=True, scaling=c["scaling"], vs_baseline=None, dtype="f32+int64",
+                    higher_is_better=True, scaling=c["scaling"], vs_baseline=None, dtype="i8->i64+f32",
                     data="synthetic", config=workload_config(c, world), e2e=m.pop("e2e"),
                     gpu_launches=m.pop("gpu_launches"), roofline=m.pop("roofline"), **m)
     main_rows = sampler.mark()

@@ -4,37 +4,43 @@
 // Replaces the second F.linear + IAFSqueeze + spikes.sum(0) of lens/run_model.py:145,238-239
 // (sinabs forward) for many independent streams.
 //
-// Exactness on tensor cores ("digit planes"): every output weight is a 47-bit signed fixed-point
-// integer m (snn.cu) = sum_j d_j 256^j with balanced digits d_j in [-128, 127], j < 6.  For each
-// digit plane j one int8 x int8 -> int32 MMA (tcgen05.mma kind::i8) computes
+// Exactness on tensor cores ("digit planes"): every output weight is a signed fixed-point integer m (snn.cu,
+// |m| < 2^46 before the row's common trailing zero bits are shifted into its scale) = sum_j d_j 256^j with
+// balanced digits d_j in [-128, 127], j < 6.  For each digit plane j one int8 x int8 -> int32 MMA
+// (tcgen05.mma kind::i8) computes
 //     P_j[place][step] = sum_k d_j[place][k] * s1[step][k]          (|P_j| < 2^22, exact)
-// and the epilogue recombines X = sum_j P_j 256^j in int64, rounds ONCE to fp32 (cvt.rn.f32.s64)
-// and scales by the row's 2^q: bit-identical to the event-driven kernel and to the CPU oracle.
+// and the epilogue recombines X = sum_j P_j 256^j in int64 and rounds ONCE to fp32 (cvt.rn.f32.s64); the
+// row's 2^q is applied by the scan's first FMA (exact product): bit-identical to the event-driven kernel and
+// to the CPU oracle.  Place tiles whose top plane is all zero (npl = 5: rows whose weights span <= 15 binary
+// orders of magnitude) skip that plane's operand loads, MMAs and drains.
 //
-// Mapping: M = 128 places (TMEM lanes), N = 64 columns = 32 consecutive timesteps of TWO streams
-// (column 2n + s = step n of stream s), K = F padded to 32.  Time runs along the columns,
-// so a thread owns one place and scans the columns of a stream serially with the membrane potential
-// and spike count in registers -- the recurrence never leaves the register file for a whole stream.
-// A CTA owns one place tile for the whole launch: its 6 digit planes (6 x 128 x Fp bytes, canonical
-// no-swizzle K-major core-matrix layout) stay resident in shared memory; hidden-spike pair tiles
-// (64 x Fp bytes, written by the feature kernel directly in the canonical layout) stream in through
-// a cp.async.bulk (TMA) ring.  TMEM holds the 6 x 64-column int32 accumulator set plus two 64-column
-// fp32 exchange buffers (512 columns in total).
+// Mapping: M = 128 places (TMEM lanes), N = 64 columns = up to 32 consecutive timesteps of TWO streams
+// (column 2n + s = step n of stream s; chunks never straddle a query), K = F padded to 32.  Time runs along
+// the columns, so a thread owns one place and scans the columns serially with the membrane potentials and
+// spike counts in registers.  The digit planes of the current place tile (<= 6 x 128 x Fp bytes, canonical
+// no-swizzle K-major core-matrix layout) sit in shared memory; hidden-spike pair tiles (64 x Fp bytes, written
+// by the hidden-layer variant of this kernel directly in the canonical layout) stream in through a
+// cp.async.bulk (TMA) ring.  TMEM holds the 6 x 64-column int32 accumulator set plus two 64-column fp32
+// exchange buffers (512 columns in total).
+// Work = (block of <= 16 stream pairs, place tile) super-items, tile fastest, dealt round-robin to the persistent
+// CTAs: CTAs running together share pair blocks, so spike tiles come from HBM once and then from L2.
 //
-// Four warpgroups (512 threads), registers redistributed with setmaxnreg (56 / 152 / 152 / 152):
+// Four warpgroups (512 threads), registers redistributed with setmaxnreg (56 / 168 / 168 / 120):
 //   control  warp 0 = TMA producer; warps 1-3 = MMA issuers, one per plane pair (warp 1 also allocates
 //            TMEM): the ~450 cycles a warp spends per pair in tcgen05.commit and in waiting for the pair's
 //            accumulators to come back overlap the other two warps' MMAs,
-//   drain    warps 4-7 (columns 0..31 = even stream) and 8-11 (columns 32..63 = odd stream): tcgen05.ld the
+//   drain    warps 4-7 (columns 0..31 = steps 0..15 of both streams) and 8-11 (columns 32..63): tcgen05.ld the
 //            accumulators plane pair by plane pair with register double buffering (each pair goes back to
 //            its MMA warp as soon as its last load has landed), recombine X = sum_j P_j 256^j in int64,
-//            round once to fp32, scale, tcgen05.st the contraction results into an exchange buffer,
-//   scan     warps 12-15: tcgen05.ld the 64 results of every place and run the serial IAF#2 recurrence of
-//            BOTH streams of the pair as two interleaved dependency chains (FADD -> FSET -> FADD -> FMNMX
-//            -> FADD per step), spike bits per step, popcounts per query.
-// With this split the kernel runs at the tensor pipe's floor for N = 64 (42 MMAs x 48 cycles, bound by
-// the shared-memory operand fetch, plus three commits): ~2400 cycles per tile.  -DLENS_TC_PROFILE builds
-// an instrumented variant (phase clocks + a Gantt chart of three tiles; profiles/r01_tc_phase_profile.md).
+//            round once to fp32, tcgen05.st the results into an exchange buffer,
+//   scan     warps 12-15: tcgen05.ld the 64 results of every place and run the serial IAF recurrence of BOTH
+//            streams of the pair as one chain of packed f32x2 operations (output layer: FFMA2 -> {FSET, FMNMX}
+//            -> FADD2 -> FADD2 per step, spikes counted as steps minus sum of (a < 1)); the hidden-layer variant
+//            (7-operation chain with exact multi-spike counts) scans the tiles of two stream pairs together.
+// Config 3 (P = 10 000, 5-plane tiles): ~1970 cycles per tile against 35 MMAs x 48 cycles = 1680 of
+// shared-memory operand fetch (ncu: that pipe 88 % busy); drain and scan are equally close to their limits
+// (profiles/r02_tc_phase_profile.md).  -DLENS_TC_PROFILE builds an instrumented variant (phase clocks + a
+// Gantt chart of three tiles).
 #include "snn.cuh"
 
 #include <algorithm>
