@@ -218,3 +218,29 @@ def test_config5_shard_properties():
     _, _, D = ops.seqmatch_topk(S[sample].contiguous(), L, N, want_D=True)
     assert torch.equal(D.amax(dim=1), tv[sample][..., 0])
     assert torch.equal(torch.gather(D, 1, ti[sample].long().transpose(1, 2)).transpose(1, 2), tv[sample])
+
+
+@pytest.mark.parametrize("T,F,P,B,Q", [(1, 96, 130, 3, 5), (31, 63, 100, 5, 3), (32, 200, 257, 4, 2), (33, 200, 129, 7, 3),
+                                       (64, 40, 128, 2, 4), (100, 200, 1000, 9, 2), (250, 130, 300, 33, 2)])
+def test_tensor_core_path_odd_shapes(T, F, P, B, Q):
+    """Query-aligned chunking with ragged last chunks (T not a multiple of 32, T < 32), K and M padding (F, P not
+    multiples of 32 / 128), odd stream counts (phantom pair half), stream-pair blocks with an odd last pair: both
+    tensor-core layers must equal the event-driven CUDA-core kernels bit for bit, state included, over two calls."""
+    from lens_b200.network import B200Network
+    Wf, Wo = synth.weights(100, F, P, seed=T + F)
+    nets = [B200Network(torch.from_numpy(Wf), torch.from_numpy(Wo), roi=80, k=8, num_timesteps=T, max_streams=B)
+            for _ in range(2)]
+    for call in range(2):
+        pooled = cuda(synth.pixel_counts((B, Q, 100), seed=20 + call))
+        ca, ha, oa = nets[0].run_streams(pooled=pooled, mode=1, want_steps=True)
+        cb = nets[1].run_streams(pooled=pooled, mode=2)
+        assert torch.equal(ca, cb)
+        assert torch.equal(ca, oa.to(torch.float32).reshape(B, Q, T, P).sum(2))       # counts = per-step spikes summed
+        for x, y in zip(nets[0].state(), nets[1].state()):
+            assert torch.equal(x, y)
+    # and the per-step outputs of the tensor-core path (debug variant of both kernels) equal the CUDA-core ones
+    pooled = cuda(synth.pixel_counts((B, Q, 100), seed=30))
+    ca, ha, oa = nets[0].run_streams(pooled=pooled, mode=1, want_steps=True)
+    cb, hb, ob = nets[1].run_streams(pooled=pooled, mode=2, want_steps=True)
+    assert torch.equal(ca, cb) and torch.equal(ha, hb) and torch.equal(oa, ob)
+    assert nets[0].overflow() == 0 and nets[1].overflow() == 0
