@@ -126,21 +126,27 @@ __device__ __forceinline__ unsigned long long shfl_u64(unsigned long long v, int
 }
 
 __global__ void __launch_bounds__(256)
-seqmatch_topk_warp_kernel(const float *__restrict__ S, long long n_queries, int Q, int P, int L, int N,
-                          float *__restrict__ D_out, float *__restrict__ top_val, int32_t *__restrict__ top_idx)
+seqmatch_topk_warp_kernel(const float *__restrict__ S, long long n_queries, int Q, int P, int L, int N, int n_seg,
+                          int seg_len, float *__restrict__ D_out, float *__restrict__ top_val,
+                          int32_t *__restrict__ top_idx)
 {
+    // With n_seg > 1 (few queries, many places) a warp ranks only the places [seg * seg_len, (seg + 1) * seg_len) of
+    // its query and writes list `seg` of [n_seg][n_queries][N]; lens_seqmatch_topk merges the lists afterwards.
     const int lane = threadIdx.x & 31;
-    const int Qo = Q - L + 1, Po = P - L + 1;
+    const int Qo = Q - L + 1, Po_all = P - L + 1;
     const float fl = (float)L;
     const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (long long g = warp0; g < n_queries; g += n_warps) {
+    for (long long w = warp0; w < n_queries * n_seg; w += n_warps) {
+        const int seg = (int)(w / n_queries);
+        const long long g = w - (long long)seg * n_queries;
         const int b = (int)(g / Qo), q = (int)(g - (long long)b * Qo);
         const float *Sb = S + ((size_t)b * Q + q) * P;
+        const int Po = min(Po_all, (seg + 1) * seg_len);
         unsigned long long best = 0ull;                    // lane i: i-th largest key, 0 = empty
         // kUnrollR batches of 32 candidates per iteration: all their L x kUnrollR loads are issued before
         // the first use, which is what keeps enough bytes in flight per warp to approach the HBM rate
-        for (int r0 = 0; r0 < Po; r0 += 32 * kUnrollR) {
+        for (int r0 = seg * seg_len; r0 < Po; r0 += 32 * kUnrollR) {
             float acc[kUnrollR];
 #pragma unroll
             for (int u = 0; u < kUnrollR; ++u) acc[u] = 0.0f;
@@ -164,7 +170,7 @@ seqmatch_topk_warp_kernel(const float *__restrict__ S, long long n_queries, int 
                 unsigned long long key = 0ull;
                 if (r < Po) {
                     const float d = __fdiv_rn(acc[u], fl);
-                    if (D_out) D_out[((size_t)b * Po + r) * Qo + q] = d;
+                    if (D_out) D_out[((size_t)b * Po_all + r) * Qo + q] = d;
                     key = ((unsigned long long)f32_orderable(d) << 32) | (uint32_t)r;
                 }
                 const unsigned long long kth = shfl_u64(best, 31);          // current 32nd largest
@@ -191,7 +197,7 @@ seqmatch_topk_warp_kernel(const float *__restrict__ S, long long n_queries, int 
             }
         }
         if (lane < N) {
-            const size_t o = (size_t)g * N + lane;
+            const size_t o = (size_t)w * N + lane;             // w = seg * n_queries + g
             if (best == 0ull) {
                 top_val[o] = -INFINITY;
                 top_idx[o] = -1;
@@ -578,9 +584,38 @@ extern "C" int lens_seqmatch_topk(const float *S, int B, int Q, int P, int L, in
     if (B == 0) return 0;
     const long long n_queries = (long long)B * (Q - L + 1);
     if (N <= 32) {
-        const long long blocks = std::min<long long>((n_queries + 7) / 8, (long long)std::max(sm_count(), 1) * 16);
-        seqmatch_topk_warp_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(S, n_queries, Q, P, L, N, D_out,
-                                                                                  top_val, top_idx);
+        // Few queries against many places (config 5: 1 024 streams x 100 000 places) would leave most SMs without
+        // a warp: the places of a query are then split into segments ranked by different warps, and the per-segment
+        // lists are merged by the kernel that merges per-GPU lists (same order: value desc, place index desc).
+        const int Po = P - L + 1;
+        const long long sms = std::max(sm_count(), 1), want_warps = sms * 32;
+        int n_seg = 1;
+        if (n_queries < want_warps && Po >= 8192)
+            n_seg = (int)std::min<long long>(std::min<long long>(ceil_div64(want_warps, n_queries), (32 * kMergeSlots) / N),
+                                             Po / 4096);
+        n_seg = std::max(n_seg, 1);
+        const int seg_len = ceil_div(ceil_div(Po, n_seg), 32 * kUnrollR) * (32 * kUnrollR);
+        n_seg = ceil_div(Po, seg_len);
+        const long long n_work = n_queries * n_seg;
+        const long long blocks = std::min<long long>((n_work + 7) / 8, sms * 16);
+        cudaStream_t st = as_stream(stream);
+        if (n_seg == 1) {
+            seqmatch_topk_warp_kernel<<<(unsigned)blocks, 256, 0, st>>>(S, n_queries, Q, P, L, N, 1, seg_len, D_out, top_val,
+                                                                       top_idx);
+        } else {
+            // stream-ordered scratch for the per-segment lists (no synchronisation)
+            float *seg_val = nullptr;
+            int32_t *seg_idx = nullptr;
+            const size_t n_list = (size_t)n_work * N;
+            LENS_CUDA(cudaMallocAsync(&seg_val, n_list * (sizeof(float) + sizeof(int32_t)), st));   // one block: values | indices
+            seg_idx = reinterpret_cast<int32_t *>(seg_val + n_list);
+            seqmatch_topk_warp_kernel<<<(unsigned)blocks, 256, 0, st>>>(S, n_queries, Q, P, L, N, n_seg, seg_len, D_out,
+                                                                       seg_val, seg_idx);
+            LENS_LAUNCH_CHECK();
+            topn_merge_kernel<<<(unsigned)ceil_div64(n_queries, 8), 256, 0, st>>>(seg_val, seg_idx, n_seg, n_queries, N,
+                                                                                   top_val, top_idx);
+            LENS_CUDA(cudaFreeAsync(seg_val, st));
+        }
     } else {
         dim3 grid((unsigned)n_queries);
         seqmatch_topk_kernel<<<grid, kMatchThreads, 0, as_stream(stream)>>>(S, Q, P, L, N, D_out, top_val, top_idx);

@@ -721,6 +721,8 @@ extern "C" int lens_snn_destroy(void *handle)
 {
     if (!handle) return 0;
     SnnHandle *h = static_cast<SnnHandle *>(handle);
+    for (auto &t : h->timed) { cudaEventDestroy(t.start); cudaEventDestroy(t.stop); }   // uncollected timings
+    h->timed.clear();
     snn_tc_release(h);
     cudaFree(h->Wf_fx); cudaFree(h->Wf_scale); cudaFree(h->Wo_fx); cudaFree(h->Wo_scale);
     cudaFree(h->U); cudaFree(h->Uq); cudaFree(h->v0); cudaFree(h->v1); cudaFree(h->v2);

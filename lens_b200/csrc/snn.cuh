@@ -84,6 +84,9 @@ struct SnnHandle {
     std::vector<TimedLaunch> timed;
 };
 
+// pending (uncollected) timed launches kept per handle; lens_snn_get_timing empties the list
+constexpr size_t kMaxTimedLaunches = 4096;
+
 // RAII bracket: records start/stop events around a launch when timing is enabled.
 struct LaunchTimer {
     SnnHandle *h; cudaStream_t st; SnnHandle::TimedLaunch t; bool on;
@@ -98,6 +101,11 @@ struct LaunchTimer {
     {
         if (!on) return;
         cudaEventRecord(t.stop, st);
+        if (h->timed.size() >= kMaxTimedLaunches) {      // nobody collected them: forget the oldest
+            cudaEventDestroy(h->timed.front().start);
+            cudaEventDestroy(h->timed.front().stop);
+            h->timed.erase(h->timed.begin());
+        }
         h->timed.push_back(t);
     }
 };
