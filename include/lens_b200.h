@@ -7,7 +7,9 @@
  *   - every function returns int: 0 = ok, <0 = bad argument (see lens_last_error()),
  *     >0 = the cudaError_t that was raised;
  *   - every pointer is a DEVICE pointer unless it says "host"; the caller owns
- *     all buffers, the library owns only what lives inside an opaque handle;
+ *     all buffers, the library owns only what lives inside an opaque handle
+ *     (plus stream-ordered scratch, cudaMallocAsync / cudaFreeAsync on the given
+ *     stream, inside lens_seqmatch_topk when it splits the places of a query);
  *   - every function is asynchronous and ordered on the cudaStream_t it is given
  *     (pass as void*: 0 = legacy default stream); none synchronises the device;
  *   - handles are not thread-safe (one per stream / rank);
