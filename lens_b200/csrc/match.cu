@@ -125,6 +125,9 @@ __device__ __forceinline__ unsigned long long shfl_u64(unsigned long long v, int
     return ((unsigned long long)hi << 32) | lo;
 }
 
+// kSeg = false is the plain one-warp-per-query kernel (40 registers: six CTAs per SM; the segmented instantiation
+// needs 48 and would cost the large-batch case a sixth of its resident warps, measured 4.5 -> 7.8 ms on config 3)
+template <bool kSeg>
 __global__ void __launch_bounds__(256)
 seqmatch_topk_warp_kernel(const float *__restrict__ S, long long n_queries, int Q, int P, int L, int N, int n_seg,
                           int seg_len, float *__restrict__ D_out, float *__restrict__ top_val,
@@ -137,16 +140,16 @@ seqmatch_topk_warp_kernel(const float *__restrict__ S, long long n_queries, int 
     const float fl = (float)L;
     const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (long long w = warp0; w < n_queries * n_seg; w += n_warps) {
-        const int seg = (int)(w / n_queries);
-        const long long g = w - (long long)seg * n_queries;
+    for (long long w = warp0; w < (kSeg ? n_queries * n_seg : n_queries); w += n_warps) {
+        const int seg = kSeg ? (int)(w / n_queries) : 0;
+        const long long g = kSeg ? w - (long long)seg * n_queries : w;
         const int b = (int)(g / Qo), q = (int)(g - (long long)b * Qo);
         const float *Sb = S + ((size_t)b * Q + q) * P;
-        const int Po = min(Po_all, (seg + 1) * seg_len);
+        const int Po = kSeg ? min(Po_all, (seg + 1) * seg_len) : Po_all;
         unsigned long long best = 0ull;                    // lane i: i-th largest key, 0 = empty
         // kUnrollR batches of 32 candidates per iteration: all their L x kUnrollR loads are issued before
         // the first use, which is what keeps enough bytes in flight per warp to approach the HBM rate
-        for (int r0 = seg * seg_len; r0 < Po; r0 += 32 * kUnrollR) {
+        for (int r0 = kSeg ? seg * seg_len : 0; r0 < Po; r0 += 32 * kUnrollR) {
             float acc[kUnrollR];
 #pragma unroll
             for (int u = 0; u < kUnrollR; ++u) acc[u] = 0.0f;
@@ -600,8 +603,8 @@ extern "C" int lens_seqmatch_topk(const float *S, int B, int Q, int P, int L, in
         const long long blocks = std::min<long long>((n_work + 7) / 8, sms * 16);
         cudaStream_t st = as_stream(stream);
         if (n_seg == 1) {
-            seqmatch_topk_warp_kernel<<<(unsigned)blocks, 256, 0, st>>>(S, n_queries, Q, P, L, N, 1, seg_len, D_out, top_val,
-                                                                       top_idx);
+            seqmatch_topk_warp_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(S, n_queries, Q, P, L, N, 1, seg_len, D_out,
+                                                                              top_val, top_idx);
         } else {
             // stream-ordered scratch for the per-segment lists (no synchronisation)
             float *seg_val = nullptr;
@@ -609,8 +612,8 @@ extern "C" int lens_seqmatch_topk(const float *S, int B, int Q, int P, int L, in
             const size_t n_list = (size_t)n_work * N;
             LENS_CUDA(cudaMallocAsync(&seg_val, n_list * (sizeof(float) + sizeof(int32_t)), st));   // one block: values | indices
             seg_idx = reinterpret_cast<int32_t *>(seg_val + n_list);
-            seqmatch_topk_warp_kernel<<<(unsigned)blocks, 256, 0, st>>>(S, n_queries, Q, P, L, N, n_seg, seg_len, D_out,
-                                                                       seg_val, seg_idx);
+            seqmatch_topk_warp_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(S, n_queries, Q, P, L, N, n_seg, seg_len, D_out,
+                                                                             seg_val, seg_idx);
             LENS_LAUNCH_CHECK();
             topn_merge_kernel<<<(unsigned)ceil_div64(n_queries, 8), 256, 0, st>>>(seg_val, seg_idx, n_seg, n_queries, N,
                                                                                    top_val, top_idx);
