@@ -203,6 +203,10 @@ int lens_recall_bounds(const float *D, const uint8_t *GT, int Po, int Qo, const 
  *   gtp    [1] i64 device: number of queries that have a positive at all (GT.any(0))             */
 int lens_pr_counts(const float *S, const uint8_t *GT, int Po, int Qo, int n_thresh, int64_t *tp,
                    int64_t *fp, int64_t *gtp, void *stream);
+/* The same for matching='multi' (lens/src/metrics.py:63-91): every entry of S counts, thresholds are
+ * np.linspace(S.max(), S.min(), n_thresh), gtp = count_nonzero(GT).  tp, fp, gtp are overwritten.          */
+int lens_pr_counts_multi(const float *S, const uint8_t *GT, int Po, int Qo, int n_thresh, int64_t *tp,
+                         int64_t *fp, int64_t *gtp, void *stream);
 
 /* Sum-of-absolute-differences baseline, lens/src/sad.py:25-42: dist[q][r] = sum_p |a[q][p] - b[r][p]|
  * (torch.cdist(a, b, p=1) on float32 copies of uint8 frames; the sums are integers < 2^24, hence exact

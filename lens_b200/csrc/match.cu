@@ -438,6 +438,54 @@ __global__ void __launch_bounds__(256) pr_counts_kernel(const float *__restrict_
     if (threadIdx.x == 0) gtp[0] = s_gtp;
 }
 
+// createPR, matching = 'multi' (lens/src/metrics.py:63-91): every entry of the matrix counts.  Pass 1: extreme
+// values (as order-preserving integers) and the number of ground-truth positives; pass 2: one CTA per (threshold,
+// slice of the matrix) counts the entries >= threshold that are / are not positives.  Thresholds as in the
+// 'single' kernel: np.linspace(max, min, n) evaluated in float64 without FMA contraction.
+__global__ void __launch_bounds__(256) pr_multi_minmax_kernel(const float *__restrict__ S, const uint8_t *__restrict__ GT,
+                                                              long long n, unsigned int *__restrict__ mm,
+                                                              unsigned long long *__restrict__ gtp)
+{
+    unsigned int vmax = 0u, vmin = 0xffffffffu;
+    unsigned long long pos = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const unsigned int k = f32_orderable(S[i]);
+        vmax = max(vmax, k); vmin = min(vmin, k);
+        pos += GT[i] != 0;
+    }
+    vmax = __reduce_max_sync(0xffffffffu, vmax);
+    vmin = __reduce_min_sync(0xffffffffu, vmin);
+    for (int o = 16; o > 0; o >>= 1) pos += __shfl_xor_sync(0xffffffffu, pos, o);
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(mm, vmax);
+        atomicMin(mm + 1, vmin);
+        if (pos) atomicAdd(gtp, pos);
+    }
+}
+
+__global__ void __launch_bounds__(256) pr_multi_counts_kernel(const float *__restrict__ S, const uint8_t *__restrict__ GT,
+                                                              long long n, int n_thresh, const unsigned int *__restrict__ mm,
+                                                              unsigned long long *__restrict__ tp,
+                                                              unsigned long long *__restrict__ fp)
+{
+    const int i = blockIdx.x;
+    const double start = (double)f32_from_orderable(mm[0]), stop = (double)f32_from_orderable(mm[1]);
+    const double step = __ddiv_rn(__dsub_rn(stop, start), (double)(n_thresh - 1));
+    const double t = (i == n_thresh - 1) ? stop : __dadd_rn(__dmul_rn((double)i, step), start);
+    const long long per = ceil_div64(n, gridDim.y), e0 = per * blockIdx.y, e1 = min(n, e0 + per);
+    unsigned long long a = 0, b = 0;
+    for (long long e = e0 + threadIdx.x; e < e1; e += blockDim.x)
+        if ((double)S[e] >= t) { if (GT[e]) ++a; else ++b; }
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (a) atomicAdd(tp + i, a);
+        if (b) atomicAdd(fp + i, b);
+    }
+}
+
 // SAD baseline (lens/src/sad.py:38): one warp per (query, reference) pair, 16 pixels per lane-iteration
 // with byte-wise SIMD sum of absolute differences; integer accumulation (exact), stored as fp32.
 __global__ void __launch_bounds__(256) sad_kernel(const uint8_t *__restrict__ a, const uint8_t *__restrict__ b,
@@ -686,5 +734,31 @@ extern "C" int lens_topn_merge(const float *val, const int32_t *idx, int W, int6
     LENS_CHECK_ARG(val && idx && out_val && out_idx, "lens_topn_merge: NULL buffer");
     topn_merge_kernel<<<(unsigned)ceil_div64(M, 8), 256, 0, as_stream(stream)>>>(val, idx, W, M, N, out_val, out_idx);
     LENS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int lens_pr_counts_multi(const float *S, const uint8_t *GT, int Po, int Qo, int n_thresh, int64_t *tp,
+                                    int64_t *fp, int64_t *gtp, void *stream)
+{
+    LENS_CHECK_ARG(Po > 0 && Qo > 0, "lens_pr_counts_multi: bad sizes");
+    LENS_CHECK_ARG(n_thresh > 1 && n_thresh <= 65535, "lens_pr_counts_multi: n_thresh must be in (1, 65535]");
+    LENS_CHECK_ARG(S && GT && tp && fp && gtp, "lens_pr_counts_multi: NULL buffer");
+    cudaStream_t st = as_stream(stream);
+    const long long n = (long long)Po * Qo;
+    unsigned int *mm = nullptr;                       // {max, min} of S as order-preserving integers
+    LENS_CUDA(cudaMallocAsync(&mm, 2 * sizeof(unsigned int), st));
+    LENS_CUDA(cudaMemsetAsync(mm, 0x00, sizeof(unsigned int), st));
+    LENS_CUDA(cudaMemsetAsync(mm + 1, 0xff, sizeof(unsigned int), st));
+    LENS_CUDA(cudaMemsetAsync(tp, 0, (size_t)n_thresh * sizeof(int64_t), st));
+    LENS_CUDA(cudaMemsetAsync(fp, 0, (size_t)n_thresh * sizeof(int64_t), st));
+    LENS_CUDA(cudaMemsetAsync(gtp, 0, sizeof(int64_t), st));
+    const int blocks = (int)std::min<long long>(ceil_div64(n, 256), (long long)std::max(sm_count(), 1) * 8);
+    pr_multi_minmax_kernel<<<blocks, 256, 0, st>>>(S, GT, n, mm, reinterpret_cast<unsigned long long *>(gtp));
+    LENS_LAUNCH_CHECK();
+    const int slices = (int)std::max<long long>(1, std::min<long long>(ceil_div64(n, 65536), 64));
+    pr_multi_counts_kernel<<<dim3((unsigned)n_thresh, (unsigned)slices), 256, 0, st>>>(
+        S, GT, n, n_thresh, mm, reinterpret_cast<unsigned long long *>(tp), reinterpret_cast<unsigned long long *>(fp));
+    LENS_LAUNCH_CHECK();
+    LENS_CUDA(cudaFreeAsync(mm, st));
     return 0;
 }

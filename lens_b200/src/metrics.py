@@ -89,18 +89,16 @@ def recallAtK(S_in, GThard, GTsoft=None, K=1):
 
 
 def createPR(S_in, GThard, outputdir=None, datatype="LENS", GTsoft=None, matching="multi", n_thresh=100):
-    """Precision / recall lists of lens/src/metrics.py:21-139 for matching='single' (the only mode the
-    reference's inference path uses, lens/run_model.py:321).  S_in, GThard: numpy [database, query].
-    Returns (P, R): python lists of length n_thresh + 1 starting with P = 1, R = 0.  The figure the
-    reference saves on the last threshold is not produced."""
+    """Precision / recall lists of lens/src/metrics.py:21-139: matching='single' (best match per query, the mode
+    the reference's inference path uses, lens/run_model.py:321) or 'multi' (every entry of the matrix, the
+    reference's default).  S_in, GThard: numpy [database, query].  Returns (P, R): python lists of length
+    n_thresh + 1 starting with P = 1, R = 0.  The figure the reference saves on the last threshold is not produced."""
     from .._lib import lib, check, ptr, stream_ptr
     S_in, GThard = np.asarray(S_in), np.asarray(GThard)
     assert S_in.shape == GThard.shape, "S_in, GThard and GTsoft must have the same shape"
     assert S_in.ndim == 2, "S_in, GThard and GTsoft must be two-dimensional"
     assert matching in ("single", "multi"), "matching should contain one of the following strings: [single, multi]"
     assert n_thresh > 1, "n_thresh must be >1"
-    if matching != "single":
-        raise NotImplementedError("lens_b200 implements createPR for matching='single' only")
     GT = GThard.astype(bool)
     S = S_in.astype(np.float32, copy=True)
     if GTsoft is not None:
@@ -112,8 +110,12 @@ def createPR(S_in, GThard, outputdir=None, datatype="LENS", GTsoft=None, matchin
     tp = torch.zeros(n_thresh, dtype=torch.int64, device="cuda")
     fp = torch.zeros(n_thresh, dtype=torch.int64, device="cuda")
     gtp = torch.zeros(1, dtype=torch.int64, device="cuda")
-    check(lib().lens_pr_counts(ptr(dS), ptr(dG), Po, Qo, n_thresh, ptr(tp), ptr(fp), ptr(gtp), stream_ptr()),
-          "lens_pr_counts")
+    if matching == "single":
+        check(lib().lens_pr_counts(ptr(dS), ptr(dG), Po, Qo, n_thresh, ptr(tp), ptr(fp), ptr(gtp), stream_ptr()),
+              "lens_pr_counts")
+    else:
+        check(lib().lens_pr_counts_multi(ptr(dS), ptr(dG), Po, Qo, n_thresh, ptr(tp), ptr(fp), ptr(gtp), stream_ptr()),
+              "lens_pr_counts_multi")
     tp, fp, gtp = tp.cpu().numpy(), fp.cpu().numpy(), int(gtp.item())
     P, R = [1], [0]
     with np.errstate(divide="ignore", invalid="ignore"):

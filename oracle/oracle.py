@@ -270,17 +270,24 @@ def evaluate_tail(S, GT, L, tol, Ns=(1, 5, 10, 15, 20, 25), kind=None):
     return D, GTtol, R
 
 
-def create_pr(S_in, GThard, n_thresh=100):
-    """createPR(..., matching='single') of lens/src/metrics.py:21-139 without the figure -> (P, R) lists."""
-    S, GT = np.asarray(S_in), np.asarray(GThard).astype(bool)
-    gtp = np.count_nonzero(GT.any(0))
-    best_row = np.argmax(S, axis=0)
-    hit = GT[best_row, np.arange(GT.shape[1])]
-    best = np.max(S, axis=0)
+def create_pr(S_in, GThard, n_thresh=100, matching="single", GTsoft=None):
+    """createPR of lens/src/metrics.py:21-139 without the figure -> (P, R) lists.
+    matching='single': best match per query (:59-68); 'multi': every entry of the matrix (:70-72)."""
+    S, GT = np.asarray(S_in).copy(), np.asarray(GThard).astype(bool)
+    if GTsoft is not None:
+        S[np.asarray(GTsoft).astype(bool) & ~GT] = S.min()
+    if matching == "single":
+        gtp = np.count_nonzero(GT.any(0))
+        best_row = np.argmax(S, axis=0)
+        hit = GT[best_row, np.arange(GT.shape[1])]
+        val = np.max(S, axis=0)
+    else:
+        gtp = np.count_nonzero(GT)
+        hit, val = GT, S
     P, R = [1], [0]
     with np.errstate(divide="ignore", invalid="ignore"):
-        for t in np.linspace(best.max(), best.min(), n_thresh):
-            sel = best >= t
+        for t in np.linspace(val.max(), val.min(), n_thresh):
+            sel = val >= t
             tp, fp = np.count_nonzero(hit & sel), np.count_nonzero(~hit & sel)
             P.append(np.float64(tp) / np.float64(tp + fp))
             R.append(np.float64(tp) / np.float64(gtp))

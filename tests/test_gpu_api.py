@@ -192,6 +192,25 @@ def test_createPR_matches_reference(golden):
         assert np.array_equal(np.array(R, dtype=np.float64), g["PR_R"], equal_nan=True)
 
 
+def test_createPR_multi_matches_reference(golden):
+    """CUDA createPR(matching='multi'), the reference's default mode: the reference's own lists on both bundled
+    runs (n_thresh 100 and 7), with a soft ground truth, and on a small matrix full of ties."""
+    from lens_b200.src.metrics import createPR
+    pm = golden("pr_multi")
+
+    def same(got, key):
+        P, R = got
+        assert np.array_equal(np.array(P, dtype=np.float64), pm[key + "/P"], equal_nan=True), key
+        assert np.array_equal(np.array(R, dtype=np.float64), pm[key + "/R"], equal_nan=True), key
+    for name in ("config1", "brisevent"):
+        g = golden(name)
+        S, GT = g["D"].T, g["GTtol"].T
+        for n in (100, 7):
+            same(createPR(S, GT, None, matching="multi", n_thresh=n), f"{name}/n{n}")
+        same(createPR(S, GT, None, GTsoft=np.roll(GT, 1, axis=1) | GT, matching="multi", n_thresh=50), f"{name}/soft")
+    same(createPR(pm["random/S"], pm["random/GT"], None, n_thresh=20), "random")      # 'multi' is the default
+
+
 def test_pr_curve_flag(example_tree, monkeypatch):
     from lens_b200.config import default_args, generate_model_name
     from lens_b200.run_model import LENS, run_inference

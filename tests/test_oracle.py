@@ -325,3 +325,22 @@ def test_evaluate_tail_option_space(golden):
             assert got == want, (key, K)                                  # same numpy, same unstable argsort
         n += 1
     assert n == 7
+
+
+def test_create_pr_multi_matches_reference(golden):
+    """The oracle's createPR(matching='multi') == the reference's own lists (tests/golden/make_golden_pr_multi.py)."""
+    pm = golden("pr_multi")
+    for name in ("config1", "brisevent"):
+        g = golden(name)
+        S, GT = g["D"].T, g["GTtol"].T
+        for n in (100, 7):
+            P, R = O.create_pr(S, GT, n_thresh=n, matching="multi")
+            assert np.array_equal(np.array(P, np.float64), pm[f"{name}/n{n}/P"], equal_nan=True)
+            assert np.array_equal(np.array(R, np.float64), pm[f"{name}/n{n}/R"], equal_nan=True)
+        soft = np.roll(GT, 1, axis=1) | GT
+        P, R = O.create_pr(S, GT, n_thresh=50, matching="multi", GTsoft=soft)
+        assert np.array_equal(np.array(P, np.float64), pm[f"{name}/soft/P"], equal_nan=True)
+        assert np.array_equal(np.array(R, np.float64), pm[f"{name}/soft/R"], equal_nan=True)
+    P, R = O.create_pr(pm["random/S"], pm["random/GT"], n_thresh=20, matching="multi")
+    assert np.array_equal(np.array(P, np.float64), pm["random/P"], equal_nan=True)
+    assert np.array_equal(np.array(R, np.float64), pm["random/R"], equal_nan=True)
